@@ -1,0 +1,377 @@
+"""Pins for the CPU oracle: the reference has no tests or
+golden vectors and cannot run here, so the oracle is pinned by identities and
+independent physics."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import symmetry as sym
+from oracle.philox import philox4x32_10, sweep_randoms
+
+
+def _models(dtype=np.float64, scale=0.1):
+    rng = np.random.default_rng(7)
+    return [oracle.CRBM(5, 2, 4, 2, rng=rng, scale=scale, dtype=dtype),
+            oracle.CRBM(3, 1, 2, 2, rng=rng, scale=scale, dtype=dtype),
+            oracle.DCRBM(3, [4, 4, 4], 2, rng=rng, scale=scale, dtype=dtype),
+            oracle.DCRBM(3, [6, 2], 2, rng=rng, scale=scale, dtype=dtype)]
+
+
+def _states(rng, n, L):
+    return rng.integers(0, 2, (n, L * L)).astype(np.int32) * 2 - 1
+
+
+# 1 ---------------------------------------------------------------------
+@pytest.mark.parametrize("shape,p", [((6, 6), (2, 2)), ((5, 7), (3, 1)), ((8,), (3,)),
+                                     ((3, 4, 5), (1, 2, 2))])
+def test_pad_is_numpy_wrap(shape, p):
+    rng = np.random.default_rng(0)
+    x = rng.integers(-5, 5, (3,) + shape)
+    want = np.pad(x, [(0, 0)] + [(q, q) for q in p], mode="wrap")
+    got = oracle.pad(x, shape, p)
+    assert np.array_equal(got, want)
+    assert np.array_equal(oracle.unpad(got, p), x)
+
+
+def test_index_matrix_offsets():
+    # window (w-1)//2 offset, row-major window order, periodic wrap (helpers.py:28-32)
+    im = oracle.create_index_matrix((4, 5), (3, 3))
+    assert im.shape == (20, 9) and im.dtype == np.int32
+    # site (0,0): rows -1,0,1 x cols -1,0,1
+    assert list(im[0]) == [3 * 5 + 4, 15, 16, 4, 0, 1, 9, 5, 6]
+    im2 = oracle.create_index_matrix((6,), (4,))          # even window: offset 1
+    assert list(im2[0]) == [5, 0, 1, 2]
+
+
+def test_interactions_are_forward_neighbours():
+    L = 4
+    s = _states(np.random.default_rng(1), 3, L)
+    it = oracle.interactions(s, (L, L))
+    g = s.reshape(3, L, L)
+    assert np.array_equal(it[:, 0].reshape(3, L, L), g * np.roll(g, -1, 1))
+    assert np.array_equal(it[:, 1].reshape(3, L, L), g * np.roll(g, -1, 2))
+
+
+def test_gather_update_windows_roundtrip():
+    L = 5
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((4, L * L))
+    centers = rng.integers(0, L * L, 4)
+    w = oracle.gather_windows(x, centers, (L, L), (3, 3))
+    assert np.array_equal(w, oracle.all_windows(x, (L, L), (3, 3))[np.arange(4), centers])
+    mask = np.array([True, False, True, False])
+    y = oracle.update_windows(x, centers, -w, mask, (L, L), (3, 3))
+    w2 = oracle.gather_windows(y, centers, (L, L), (3, 3))
+    assert np.array_equal(w2[mask], -w[mask]) and np.array_equal(y[~mask], x[~mask])
+
+
+# 2 ---------------------------------------------------------------------
+def _brute_log_ratio(model, states, L, flips):
+    """log psi(s with `flips` flipped) - log psi(s), full lattice, float64."""
+    halo = (model.r - 1) // 2
+    def lp(s):
+        return model.log_psi(oracle.pad(s.reshape(-1, L, L), (L, L), [halo, halo]))
+    s2 = states.copy()
+    for f in flips:
+        s2[:, f] *= -1
+    return lp(s2) - lp(states)
+
+
+@pytest.mark.parametrize("L", [6, 8])
+def test_window_trick_matches_brute_force_tfim(L):
+    rng = np.random.default_rng(11)
+    for model in _models():
+        if model.r > L:
+            continue
+        s = _states(rng, 3, L)
+        e = oracle.ising_energy(model, s, (L, L), model.r, H=0.7)
+        ratios = np.stack([np.exp(_brute_log_ratio(model, s, L, [i]))
+                           for i in range(L * L)], 1)
+        g = s.reshape(-1, L, L)
+        aligned = (g * np.roll(g, -1, 1)).sum((1, 2)) + (g * np.roll(g, -1, 2)).sum((1, 2))
+        want = (-0.7 * ratios.sum(1) - aligned) / (L * L)
+        assert np.abs(e - want).max() < 1e-11
+
+
+@pytest.mark.parametrize("L", [8])
+def test_window_trick_matches_brute_force_heisenberg(L):
+    rng = np.random.default_rng(12)
+    for model in _models():
+        if model.r + 2 > L:
+            continue
+        s = _states(rng, 2, L)
+        e = oracle.heisenberg_energy(model, s, (L, L), model.r)
+        idx = np.arange(L * L).reshape(L, L)
+        total = np.zeros(2, complex)
+        for d in range(2):
+            nb = np.roll(idx, -1, d).ravel()
+            for i in range(L * L):
+                sisj = s[:, i] * s[:, nb[i]]
+                ratio = np.exp(_brute_log_ratio(model, s, L, [i, nb[i]]))
+                total += -(1 - sisj) * ratio + sisj
+        assert np.abs(e - total / (L * L)).max() < 1e-11
+
+
+# 3, 4 ------------------------------------------------------------------
+def test_log_psi_translation_invariant():
+    L = 6
+    rng = np.random.default_rng(5)
+    for model in _models():
+        if model.r > L:
+            continue
+        halo = (model.r - 1) // 2
+        s = _states(rng, 2, L).reshape(-1, L, L)
+        base = model.log_psi(oracle.pad(s, (L, L), [halo, halo]))
+        for a, b in itertools.product(range(L), range(L)):
+            sh = np.roll(s, (a, b), (1, 2))
+            v = model.log_psi(oracle.pad(sh, (L, L), [halo, halo]))
+            assert np.abs(v - base).max() < 1e-12 * max(1.0, np.abs(base).max())
+
+
+def test_d4_filter_fold_identity():
+    """psi(g.s; W) == psi(s; W o g) for the 8 point-group elements."""
+    L = 6
+    rng = np.random.default_rng(6)
+    model = oracle.CRBM(5, 2, 3, 2, rng=rng, scale=0.2, dtype=np.float64)
+    s = _states(rng, 3, L)
+    images = sym.d4_filter_images(model.params["filters"])
+    for p, g in enumerate(sym.d4(L)):
+        gs = s[:, sym.site_permutation(g, L)].reshape(-1, L, L)
+        lhs = model.log_psi(oracle.pad(gs, (L, L), [2, 2]))
+        folded = model.astype(np.float64)
+        folded.params = dict(model.params, filters=images[p])
+        rhs = folded.log_psi(oracle.pad(s.reshape(-1, L, L), (L, L), [2, 2]))
+        assert np.abs(lhs - rhs).max() < 1e-12
+    # and the full 8 L^2 average equals the 8-image average
+    a = sym.symmetrised_log_psi(model, s, (L, L), full_group=True)
+    b = sym.symmetrised_log_psi(model, s, (L, L), full_group=False)
+    assert np.abs(np.exp(a - b) - 1).max() < 1e-12
+
+
+# 5 ---------------------------------------------------------------------
+def test_notebook_group_axioms_M4():
+    M = 4
+    D4, T, G = sym.d4(M), sym.translations(M), sym.group(M)
+    keys = {g.tobytes() for g in G}
+    assert len(keys) == 8 * M * M == len(G)
+    assert len({g.tobytes() for g in D4}) == 8 and len({t.tobytes() for t in T}) == M * M
+    for a, b in itertools.product(G, G):                       # closure
+        assert sym.mod(a @ b, M).tobytes() in keys
+    eye = np.eye(3, dtype=np.int64)
+    tkeys = {t.tobytes() for t in T}
+    for g in G:                                                 # inverse
+        gi = sym.mod(sym.inv(g), M)
+        assert gi.tobytes() in keys
+        assert np.array_equal(sym.mod(gi @ g, M), eye) and np.array_equal(sym.mod(g @ gi, M), eye)
+    sub = G[:: 7]                                               # associativity (sampled: O(|G|^3))
+    for a, b, c in itertools.product(sub, sub, sub):
+        assert np.array_equal(sym.mod(a @ sym.mod(b @ c, M), M), sym.mod(sym.mod(a @ b, M) @ c, M))
+    for t, g in itertools.product(T, G):                        # T normal in G
+        assert sym.mod(sym.mod(g @ t, M) @ sym.inv(g), M).tobytes() in tkeys
+    ident = sym.neighbours(sym.plot(T[0], M), M)
+    for g in G:                                                 # bijection, neighbour-preserving
+        grid = sym.plot(g, M)
+        assert (grid == -1).sum() == 0
+        assert sym.neighbours(grid, M) == ident
+    assert {g.tobytes() for g in sym.product(T, D4, M)} == keys  # T.D4 == D4.T as sets
+
+
+def test_notebook_neighbours_cell2_M10():
+    M = 10
+    D4, T = sym.d4(M), sym.translations(M)
+    for g in (sym.mod(D4[7] @ T[5], M), sym.mod(D4[7] @ T[45], M), sym.mod(D4[3] @ T[99], M)):
+        assert sym.neighbours(sym.plot(g, M), M)[12] == [2, 11, 13, 22]
+    # the stored cell-1 grid is D4[7].T[45] (the cell is stale)
+    grid = sym.plot(sym.mod(D4[7] @ T[45], M), M)
+    assert list(grid[0]) == [65, 55, 45, 35, 25, 15, 5, 95, 85, 75]
+    assert list(grid[:, 0]) == [65, 64, 63, 62, 61, 60, 69, 68, 67, 66]
+
+
+# 6 ---------------------------------------------------------------------
+@pytest.mark.parametrize("shape,r,num_samples,want", [
+    ((6, 6), 5, 64, (64, 360, 1, 1440, 1441, (10, 10))),
+    ((10, 10), 7, 4096, (4096, 1000, 1, 4000, 4001, (16, 16))),
+    ((20, 20), 13, 4096, (4096, 4000, 1, 16000, 16001, (32, 32))),
+    ((10, 10), 5, 8192, (8192, 1000, 1, 4000, 4001, (14, 14))),
+    ((40, 40), 13, 8192, (8192, 16000, 1, 64000, 64001, (52, 52))),
+])
+def test_sampler_bookkeeping(shape, r, num_samples, want):
+    class Big(oracle.Sampler):
+        MAX_NUM_SAMPLERS = 10 ** 9
+    m = oracle.CRBM(3, 1, 1, 2)
+    s = Big(m, shape, r, num_samples, 1)
+    got = (s.num_samplers, s.its_per_sample, s.samples_per_sampler, s.therm_its,
+           s.sample_its, s.padded_shape)
+    assert got == want
+
+
+def test_sampler_bookkeeping_reference_cap():
+    m = oracle.CRBM(3, 1, 1, 2)
+    s = oracle.Sampler(m, (10, 10), 5, 3000, 2)     # capped at 1000 chains x 3 samples
+    assert (s.num_samplers, s.samples_per_sampler) == (1000, 3)
+    assert s.therm_its == 3 * 1000 * 4 and s.sample_its == 12000 + 2 * 1000 + 1
+
+
+def test_sampler_step_semantics():
+    """identity double flip always accepted; strict '>'; update-then-write;
+    output row order j*S + chain (sampler.py:114-115,125,147-152,176-177)."""
+    L, S = 4, 3
+    class Tiny(oracle.Sampler):
+        SWEEPFACTOR, THERMFACTOR = 1, 1
+    model = oracle.CRBM(3, 1, 2, 2, rng=np.random.default_rng(2), scale=0.3, dtype=np.float64)
+    smp = Tiny(model, (L, L), 3, 2 * S, 2)
+    assert (smp.num_samplers, smp.samples_per_sampler, smp.its_per_sample) == (6, 1, 16)
+    Tiny.MAX_NUM_SAMPLERS = S
+    smp = Tiny(model, (L, L), 3, 2 * S, 2)
+    assert (smp.num_samplers, smp.samples_per_sampler, smp.therm_its, smp.sample_its) == (3, 2, 32, 49)
+    rng = np.random.default_rng(4)
+    init = rng.integers(0, 2, (S, L, L)) * 2 - 1
+    pos = rng.integers(0, L * L, (smp.sample_its, S, 2)).astype(np.int32)
+    u = rng.random((smp.sample_its, S)).astype(np.float32)
+    pos[0, 0] = [5, 5]; u[0, 0] = np.float32(0.999999)         # identity proposal
+    out = smp.mcmc_op(init, pos, u)
+    assert out.shape == (2 * S, L * L)
+    # replay by brute force
+    cur = init.reshape(S, -1).copy()
+    lp = lambda s: model.log_psi(oracle.pad(s.reshape(-1, L, L), (L, L), [1, 1]))
+    written = {}
+    for i in range(smp.sample_its):
+        prop = cur.copy()
+        for f in range(2):
+            prop[np.arange(S), pos[i, :, f]] *= -1
+        acc = np.abs(np.exp(lp(prop) - lp(cur))) ** 2 > u[i]
+        if i == 0:
+            assert acc[0]
+        cur[acc] = prop[acc]
+        k = i - smp.therm_its
+        if k >= 0 and k % smp.its_per_sample == 0:
+            written[k // smp.its_per_sample] = cur.copy()
+    assert np.array_equal(out[:S], written[0]) and np.array_equal(out[S:], written[1])
+    # the padded state stays a consistent periodic image
+    g = smp.unpadded_current().reshape(S, L, L)
+    assert np.array_equal(oracle.pad(g, (L, L), [1, 1]).reshape(S, -1), smp.current_samples)
+
+
+# 7 ---------------------------------------------------------------------
+def _dense_h(L, kind, h=1.0):
+    """Dense Hamiltonian in the s^z basis (independent of the reference).
+    TFIM: -sum_<ij> sz sz - h sum sx.  Heisenberg: sum_<ij> sigma.sigma with the
+    Marshall sign rotation on sublattice A (off-diagonal elements -> -2)."""
+    n = L * L
+    dim = 1 << n
+    idx = np.arange(n).reshape(L, L)
+    bonds = [(i, int(np.roll(idx, -1, d).ravel()[i])) for d in range(2) for i in range(n)]
+    Hm = np.zeros((dim, dim))
+    conf = ((np.arange(dim)[:, None] >> np.arange(n)[None, :]) & 1) * 2 - 1
+    for a in range(dim):
+        s = conf[a]
+        if kind == "tfim":
+            Hm[a, a] = -sum(s[i] * s[j] for i, j in bonds)
+            for i in range(n):
+                Hm[a, a ^ (1 << i)] += -h
+        else:
+            for i, j in bonds:
+                Hm[a, a] += s[i] * s[j]
+                if s[i] != s[j]:
+                    Hm[a, a ^ (1 << i) ^ (1 << j)] += -2.0
+    return Hm, conf
+
+
+def test_local_energy_matches_dense_hamiltonian_3x3(kind="tfim"):
+    L = 3
+    rng = np.random.default_rng(9)
+    model = oracle.CRBM(3, 1, 2, 2, rng=rng, scale=0.3, dtype=np.float64)
+    Hm, conf = _dense_h(L, kind, h=0.8)
+    psi = np.exp(model.log_psi(oracle.pad(conf.reshape(-1, L, L), (L, L), [1, 1])))
+    want = (Hm @ psi) / psi / (L * L)
+    # (Heisenberg needs windows K+2 = 5 > L = 3, which alias: see the 4x4 test below)
+    got = oracle.ising_energy(model, conf, (L, L), 3, H=0.8)
+    assert np.abs(got - want).max() < 1e-10
+    # variational bound from the same amplitudes
+    e0 = np.linalg.eigvalsh(Hm)[0] / (L * L)
+    p = np.abs(psi) ** 2
+    assert (p * want.real).sum() / p.sum() >= e0 - 1e-12
+
+
+def test_heisenberg_local_energy_matches_dense_4x4_sparse():
+    """4x4 Heisenberg: check E_loc on random configurations against <s|H|psi>/<s|psi>
+    built bond by bond (no 65536^2 matrix)."""
+    L = 4
+    rng = np.random.default_rng(10)
+    model = oracle.CRBM(3, 1, 2, 2, rng=rng, scale=0.3, dtype=np.float64)
+    s = _states(rng, 6, L)
+    got = oracle.heisenberg_energy(model, s, (L, L), 3)
+    lp = lambda x: model.log_psi(oracle.pad(x.reshape(-1, L, L), (L, L), [1, 1]))
+    idx = np.arange(L * L).reshape(L, L)
+    want = np.zeros(6, complex)
+    for d in range(2):
+        nb = np.roll(idx, -1, d).ravel()
+        for i in range(L * L):
+            j = nb[i]
+            sisj = s[:, i] * s[:, j]
+            fl = s.copy(); fl[:, i] *= -1; fl[:, j] *= -1
+            want += np.where(sisj == 1, 1.0, -1.0 - 2.0 * np.exp(lp(fl) - lp(s)))
+    assert np.abs(got - want / (L * L)).max() < 1e-10
+
+
+def test_exact_ground_states_bound_sampled_energy():
+    """ED ground-state energies per spin (scipy, independent): 2x2 / 3x3 TFIM."""
+    from scipy.sparse.linalg import eigsh
+    for L, h in ((2, 1.0), (3, 1.0)):
+        Hm, conf = _dense_h(L, "tfim", h)
+        e0 = eigsh(Hm, k=1, which="SA")[0][0] / (L * L)
+        model = oracle.CRBM(L if L % 2 else 1, (L - 1) // 2 if L % 2 else 0, 2, 2,
+                            rng=np.random.default_rng(L), scale=0.2, dtype=np.float64)
+        psi = np.exp(model.log_psi(oracle.pad(conf.reshape(-1, L, L), (L, L),
+                                              [model.pad_size] * 2)))
+        e = (psi.conj() @ Hm @ psi).real / (psi.conj() @ psi).real / (L * L)
+        assert e >= e0 - 1e-12
+
+
+# philox ----------------------------------------------------------------
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def run(c, k):
+        return [int(v) for v in philox4x32_10(np.array(c, np.uint32), np.array(k, np.uint32))]
+    assert run([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_sweep_randoms_ranges_and_independence_of_partition():
+    pos, u = sweep_randoms(1234, np.arange(10), 5, 7, 2, 400)
+    assert pos.shape == (7, 10, 2) and u.shape == (7, 10)
+    assert pos.min() >= 0 and pos.max() < 400 and u.min() >= 0 and u.max() < 1
+    p2, u2 = sweep_randoms(1234, np.arange(4, 10), 8, 4, 2, 400)
+    assert np.array_equal(p2, pos[3:, 4:]) and np.array_equal(u2, u[3:, 4:])
+
+
+# gradient / loss / adam --------------------------------------------------
+@pytest.mark.parametrize("which", ["crbm", "dcrbm"])
+def test_gradient_matches_finite_differences(which):
+    L = 4
+    rng = np.random.default_rng(21)
+    model = (oracle.CRBM(3, 1, 2, 2, rng=rng, scale=0.2, dtype=np.float64) if which == "crbm"
+             else oracle.DCRBM(3, [3, 4], 2, rng=rng, scale=0.3, dtype=np.float64))
+    halo = (model.r - 1) // 2
+    s = _states(rng, 5, L)
+    xp = oracle.pad(s.reshape(-1, L, L), (L, L), [halo, halo])
+    e = (rng.standard_normal(5) + 1j * rng.standard_normal(5))
+    g, loss = oracle.vmc_gradient(model, xp, e)
+    assert abs(loss - oracle.loss_op(model.factors(xp), e)) < 1e-12
+    flat = model.flat_params()
+    for i in rng.choice(flat.size, 12, replace=False):
+        d = np.zeros_like(flat); d[i] = 1e-6
+        model.set_flat_params(flat + d); lp = oracle.loss_op(model.factors(xp), e)
+        model.set_flat_params(flat - d); lm = oracle.loss_op(model.factors(xp), e)
+        assert abs((lp - lm) / 2e-6 - g[i]) < 1e-7
+    model.set_flat_params(flat)
+
+
+def test_adam_tf1_first_step():
+    p, m, v = oracle.adam_tf1_step(np.array([1.0]), np.array([0.5]), 0.0, 0.0, 1, lr=0.1)
+    # m = 0.05, v = 2.5e-4, lr_t = 0.1*sqrt(1e-3)/0.1
+    assert np.allclose(p, 1.0 - np.sqrt(1e-3) * 0.05 / (np.sqrt(2.5e-4) + 1e-8))
