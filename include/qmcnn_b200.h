@@ -1,0 +1,143 @@
+/*
+ * qmcnn_b200.h - C ABI of the B200-native variational-Monte-Carlo hot path.
+ *
+ * This is the drop-in boundary for the one path of dmaloneynygc/qmcnn that is
+ * accelerated: the conv-wavefunction log-psi forward, the batched Metropolis
+ * sweep, the local-energy estimators and the log-psi gradient.  The reference
+ * has no FFI of its own (pure TensorFlow-1 Python); each entry point below
+ * names the reference Python call it replaces (file:line under the reference
+ * root) and is what `qmcnn_b200/_lib.py` binds with ctypes.  INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller unless it says
+ *    "host".  The library allocates only handle-private memory (parameter
+ *    copy), freed by qmc_destroy.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*).  No
+ *    call synchronises the device, throws or aborts.
+ *  - Return 0 on success, negative qmc_status on failure; text via
+ *    qmc_last_error().  A handle is bound to one device and is not thread-safe
+ *    (the reference drives one session with parallel_iterations=1,
+ *    sampler.py:172).
+ *  - Spins are int8 +-1, UN-padded, row-major [n, Ly, Lx]; periodic wrap is
+ *    index arithmetic inside the kernels (replaces helpers.py:73-91 pad/unpad).
+ *  - Parameters are ONE flat fp32 vector in the reference's variable creation
+ *    order and HWIO filter layout:
+ *      CRBM  (models.py:19-28):  filters[k,k,1,2a], bias_vis[2], bias_hid[2a]
+ *      DCRBM (models.py:85-92):  filters_0[k,k,1,C1], bias_0[C1], filters_1[k,k,C1,C2], ...
+ *  - Complex outputs are interleaved (re, im) fp32 pairs == numpy complex64.
+ */
+#ifndef QMCNN_B200_H
+#define QMCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMC_MAX_LAYERS 16
+#define QMC_MAX_FLIPS 2
+
+typedef enum {
+    QMC_OK = 0,
+    QMC_ERR_BAD_ARGUMENT = -1,
+    QMC_ERR_UNSUPPORTED = -2, /* shape outside what the kernels cover */
+    QMC_ERR_CUDA = -3,
+    QMC_ERR_NO_DEVICE = -4
+} qmc_status;
+
+enum { QMC_MODEL_CRBM = 0, QMC_MODEL_DCRBM = 1 };
+enum { QMC_HAMILTONIAN_TFIM = 0, QMC_HAMILTONIAN_HEISENBERG = 1 };
+
+/* host struct describing models.py CRBM(k, pad, alpha, 2) / DCRBM(k, layers, 2)
+ * on a periodic Ly x Lx lattice. */
+typedef struct {
+    int32_t kind;                     /* QMC_MODEL_* */
+    int32_t k;                        /* filter side, odd */
+    int32_t n_layers;                 /* D; 1 for CRBM */
+    int32_t channels[QMC_MAX_LAYERS]; /* C_1..C_D; CRBM: channels[0] = 2*alpha.
+                                         channels[D-1] must be even */
+    int32_t Ly, Lx;                   /* system_shape */
+    int32_t reserved[4];              /* zero */
+} qmc_model_desc;
+
+typedef struct qmc_handle qmc_handle;
+
+/* models.py:11-28 / 75-92 (variable creation). `device` is a CUDA ordinal. */
+int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc /*host*/);
+int qmc_destroy(qmc_handle* h);
+const char* qmc_last_error(const qmc_handle* h); /* host string; NULL handle -> last create error */
+
+size_t qmc_num_params(const qmc_handle* h);        /* P */
+int qmc_receptive_field(const qmc_handle* h);      /* r = D(k-1)+1 */
+/* floats of activation cache per chain/sample (opaque layout) */
+size_t qmc_cache_floats(const qmc_handle* h);
+/* floats of scratch qmc_metropolis_sweep needs for S chains */
+size_t qmc_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips);
+/* floats of scratch qmc_local_energy / qmc_logpsi_backward need for N samples */
+size_t qmc_energy_workspace_floats(const qmc_handle* h, int N);
+size_t qmc_backward_workspace_floats(const qmc_handle* h, int N);
+
+/* tf.assign of the model variables (models.py:19-28, 85-92): copy P floats. */
+int qmc_set_params(qmc_handle* h, const float* params, void* stream);
+int qmc_get_params(qmc_handle* h, float* params, void* stream);
+
+/* model.factors(pad(x)) and its site sum (models.py:31-67, 95-131).
+ *   cache   [N * qmc_cache_floats]  (required; filled as a by-product and
+ *                                    reusable by the sweep / energy / backward)
+ *   factors [N, Ly*Lx] complex64 or NULL
+ *   logpsi  [N] complex64 or NULL */
+int qmc_logpsi_forward(qmc_handle* h, const int8_t* spins, int N, float* cache,
+                       float* factors, float* logpsi, void* stream);
+
+/* Sampler.mcmc_step x n_steps (sampler.py:104-155) for S independent chains,
+ * persistent in-kernel, incremental receptive-field update per proposal.
+ *   spins   [S, Ly*Lx] in/out; cache [S * qmc_cache_floats] in/out (must hold
+ *           the forward of `spins` under the CURRENT parameters: call
+ *           qmc_logpsi_forward first, as mcmc_reset does, sampler.py:85-88)
+ *   steps   step0 .. step0+n_steps-1 (global step index i of the while loop)
+ *   flip_pos [n_steps, S, num_flips] int32 and uniforms [n_steps, S] fp32
+ *           (sampler.py:95-100), or BOTH NULL -> in-kernel Philox-4x32-10
+ *           keyed (seed; chain_id0 + chain, step) - see oracle/philox.py
+ *   samples [sps, S, Ly*Lx] int8 or NULL; sample j = (i-therm_its)/its_per_sample
+ *           written after the update when i >= therm_its and
+ *           (i-therm_its) % its_per_sample == 0 (sampler.py:135-152)
+ *   accept_trace [n_steps, S] uint8 or NULL; logratio_trace [n_steps, S] fp32
+ *           (Re sum(f' - f)) or NULL; n_accept [1] uint64 (+=) or NULL. */
+int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* workspace,
+                         int S, int num_flips, int64_t step0, int64_t n_steps,
+                         const int32_t* flip_pos, const float* uniforms,
+                         uint64_t seed, int64_t chain_id0,
+                         int64_t therm_its, int64_t its_per_sample, int8_t* samples,
+                         uint8_t* accept_trace, float* logratio_trace,
+                         unsigned long long* n_accept, void* stream);
+
+/* ising_energy / heisenberg_energy (mcmc_tf.py:59-90, 93-141): local energy
+ * PER SPIN of N samples; all Ly*Lx (TFIM) or 2*Ly*Lx (Heisenberg) connected
+ * configurations evaluated as receptive-field deltas in one launch sequence.
+ *   e_loc [N] complex64; moments [4] fp64 (+=): N, sum Re E, sum Im E,
+ *   sum |E|^2, or NULL. */
+int qmc_local_energy(qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins,
+                     int N, float* workspace, float* e_loc, double* moments, void* stream);
+
+/* gradient of loss_op (mcmc_tf.py:35-56, 172-177) for given per-sample complex
+ * weights w_n: grad[p] += sum_n Re[w_n * conj(d logpsi_n / d p)], P floats in
+ * qmc_set_params order.  weights [N] complex64 = (E_n - mean E)/N reproduces
+ * d loss_op / d p. */
+int qmc_logpsi_backward(qmc_handle* h, const int8_t* spins, const float* weights, int N,
+                        float* workspace, float* grad, void* stream);
+
+/* Diagnostics (synchronous, not on the hot path): measured FP32-FMA (TFLOP/s)
+ * and MUFU ex2 (Gop/s) issue peaks of `device` - the roofline denominators
+ * MEASURED_PEAKS.json does not carry. */
+int qmc_diag_peaks(int device, double* fp32_tflops /*host*/, double* mufu_gops /*host*/);
+
+/* library build info, host string */
+const char* qmc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMCNN_B200_H */

@@ -1,0 +1,238 @@
+// qmc_api.cu - the extern "C" boundary declared in include/qmcnn_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include "qmc_host.h"
+
+using namespace qmc;
+
+static thread_local std::string g_create_err;
+
+static int fail(qmc_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+static int cuda_fail(qmc_handle* h, cudaError_t e, const char* where) {
+    std::string msg = std::string(where) + ": " + cudaGetErrorString(e);
+    if (h && !h->err.empty() && e == cudaErrorInvalidValue) msg = h->err;   // launcher's own text
+    if (h) h->err = msg; else g_create_err = msg;
+    return e == cudaErrorInvalidValue ? QMC_ERR_UNSUPPORTED : QMC_ERR_CUDA;
+}
+
+static bool build_model(const qmc_model_desc* d, DevModel& m, std::string& err) {
+    std::memset(&m, 0, sizeof(m));
+    if (d->kind != QMC_MODEL_CRBM && d->kind != QMC_MODEL_DCRBM) { err = "unknown model kind"; return false; }
+    if (d->k < 1 || d->k % 2 == 0) { err = "filter side k must be odd"; return false; }
+    if (d->n_layers < 1 || d->n_layers > QMC_MAX_LAYERS) { err = "n_layers out of range"; return false; }
+    if (d->kind == QMC_MODEL_CRBM && d->n_layers != 1) { err = "CRBM has exactly one layer"; return false; }
+    if (d->Ly < 1 || d->Lx < 1) { err = "lattice sides must be positive"; return false; }
+    for (int l = 0; l < d->n_layers; ++l)
+        if (d->channels[l] < 1) { err = "channel counts must be positive"; return false; }
+    if (d->channels[d->n_layers - 1] % 2) { err = "last layer needs an even channel count (Re/Im halves)"; return false; }
+    m.kind = d->kind; m.k = d->k; m.p = (d->k - 1) / 2; m.D = d->n_layers;
+    m.Ly = d->Ly; m.Lx = d->Lx; m.n = d->Ly * d->Lx;
+    m.r = m.D * (m.k - 1) + 1;
+    if (m.k > m.Ly || m.k > m.Lx) { err = "filter larger than the lattice"; return false; }
+    int off = 0, soff = 0, coff = 0, cin = 1;
+    m.bias_vis_off = -1; m.sp_vis_off = -1;
+    for (int l = 0; l < m.D; ++l) {
+        LayerInfo& L = m.layer[l];
+        L.cin = cin; L.cout = d->channels[l];
+        L.cinp = l == 0 ? 1 : round4(cin);
+        L.coutp = round4(L.cout);
+        L.w_off = off; off += m.k * m.k * L.cin * L.cout;
+        if (d->kind == QMC_MODEL_CRBM) { m.bias_vis_off = off; off += 2; }   // models.py:19-28 order
+        L.b_off = off; off += L.cout;
+        L.sw_off = soff; soff += m.k * m.k * L.cin * L.coutp;
+        L.sb_off = soff; soff += L.coutp;
+        if (l < m.D - 1) { L.act_off = coff; coff += L.coutp * m.n; } else L.act_off = -1;
+        cin = L.cout;
+    }
+    if (m.bias_vis_off >= 0) { m.sp_vis_off = soff; soff += 4; }
+    m.P = off;
+    m.smem_param_floats = round4(soff);
+    m.fre_off = coff; coff += round4(m.n);
+    m.fim_off = coff; coff += round4(m.n);
+    m.cache_floats = coff;
+    return true;
+}
+
+extern "C" {
+
+const char* qmc_version(void) { return "qmcnn_b200 0.1 (sm_100a)"; }
+
+int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
+    if (!out || !desc) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "null argument");
+    *out = nullptr;
+    DevModel m;
+    std::string err;
+    if (!build_model(desc, m, err)) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, err);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, QMC_ERR_NO_DEVICE, "no CUDA device: the qmcnn_b200 hot path has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "bad device ordinal");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    qmc_handle* h = new qmc_handle();
+    h->device = device; h->desc = *desc; h->m = m;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem = prop.sharedMemPerBlockOptin;
+    const char* fg = std::getenv("QMC_FORCE_GENERIC");
+    h->allow_tiled = !(fg && fg[0] == '1');
+    e = cudaMalloc(&h->d_params, sizeof(float) * (size_t)m.P);
+    if (e == cudaSuccess) e = cudaMemset(h->d_params, 0, sizeof(float) * (size_t)m.P);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(params)"); }
+    if ((size_t)m.smem_param_floats * 4 > h->max_smem) {
+        cudaFree(h->d_params); delete h;
+        return fail(nullptr, QMC_ERR_UNSUPPORTED, "parameters do not fit in shared memory");
+    }
+    *out = h;
+    return QMC_OK;
+}
+
+int qmc_destroy(qmc_handle* h) {
+    if (!h) return QMC_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->device);
+    cudaFree(h->d_params);
+    cudaSetDevice(prev);
+    delete h;
+    return QMC_OK;
+}
+
+const char* qmc_last_error(const qmc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+size_t qmc_num_params(const qmc_handle* h) { return h ? (size_t)h->m.P : 0; }
+int qmc_receptive_field(const qmc_handle* h) { return h ? h->m.r : 0; }
+size_t qmc_cache_floats(const qmc_handle* h) { return h ? (size_t)h->m.cache_floats : 0; }
+
+size_t qmc_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips) {
+    if (!h || S < 1) return 0;
+    EvalPlan pl;
+    const int slots = sweep_slots(h, S, num_flips, &pl, nullptr);
+    if (slots < 0) return 0;
+    const size_t f = (size_t)slots * pl.staging_floats;
+    return f ? f : 4;
+}
+
+size_t qmc_energy_workspace_floats(const qmc_handle* h, int N) {
+    if (!h || N < 1) return 0;
+    return (size_t)N * h->m.cache_floats + (size_t)N * energy_chunks(h) * 2;
+}
+
+size_t qmc_backward_workspace_floats(const qmc_handle* h, int N) {
+    if (!h || N < 1) return 0;
+    return backward_workspace_floats(h, N);
+}
+
+#define QMC_ENTER(h)                                                       \
+    if (!(h)) return QMC_ERR_BAD_ARGUMENT;                                 \
+    (h)->err.clear();                                                      \
+    int prev_dev_ = 0;                                                     \
+    cudaGetDevice(&prev_dev_);                                             \
+    if (prev_dev_ != (h)->device) cudaSetDevice((h)->device);
+#define QMC_LEAVE(h) if (prev_dev_ != (h)->device) cudaSetDevice(prev_dev_);
+
+int qmc_set_params(qmc_handle* h, const float* params, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (!params) rc = fail(h, QMC_ERR_BAD_ARGUMENT, "null params");
+    else {
+        cudaError_t e = cudaMemcpyAsync(h->d_params, params, sizeof(float) * (size_t)h->m.P,
+                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "set_params");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_get_params(qmc_handle* h, float* params, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (!params) rc = fail(h, QMC_ERR_BAD_ARGUMENT, "null params");
+    else {
+        cudaError_t e = cudaMemcpyAsync(params, h->d_params, sizeof(float) * (size_t)h->m.P,
+                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "get_params");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_logpsi_forward(qmc_handle* h, const int8_t* spins, int N, float* cache, float* factors,
+                       float* logpsi, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (N < 0 || (N > 0 && (!spins || !cache))) rc = fail(h, QMC_ERR_BAD_ARGUMENT, "forward: null spins/cache");
+    else if (N > 0) {
+        cudaError_t e = launch_forward(h, spins, N, cache, factors, logpsi, (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "logpsi_forward");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* workspace, int S,
+                         int num_flips, int64_t step0, int64_t n_steps, const int32_t* flip_pos,
+                         const float* uniforms, uint64_t seed, int64_t chain_id0, int64_t therm_its,
+                         int64_t its_per_sample, int8_t* samples, uint8_t* accept_trace,
+                         float* logratio_trace, unsigned long long* n_accept, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (S < 0 || n_steps < 0 || (S > 0 && (!spins || !cache || !workspace)))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep: null spins/cache/workspace");
+    else if (num_flips < 1 || num_flips > QMC_MAX_FLIPS)
+        rc = fail(h, QMC_ERR_UNSUPPORTED, "sweep: num_flips must be 1 or 2");
+    else if ((flip_pos == nullptr) != (uniforms == nullptr))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep: flip_pos and uniforms must both be given or both be NULL");
+    else if (samples && its_per_sample < 1)
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep: its_per_sample must be positive");
+    else if (S > 0 && n_steps > 0) {
+        SweepArgs a{spins, cache, workspace, S, num_flips, step0, n_steps, flip_pos, uniforms,
+                    seed, chain_id0, therm_its, its_per_sample > 0 ? its_per_sample : 1, samples,
+                    accept_trace, logratio_trace, n_accept};
+        cudaError_t e = launch_sweep(h, a, (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_local_energy(qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins, int N,
+                     float* workspace, float* e_loc, double* moments, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (N < 0 || (N > 0 && (!spins || !workspace || !e_loc)))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "local_energy: null spins/workspace/e_loc");
+    else if (hamiltonian != QMC_HAMILTONIAN_TFIM && hamiltonian != QMC_HAMILTONIAN_HEISENBERG)
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "local_energy: unknown hamiltonian");
+    else if (N > 0) {
+        cudaError_t e = launch_energy(h, hamiltonian, field_h, spins, N, workspace, e_loc, moments,
+                                      (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "local_energy");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_logpsi_backward(qmc_handle* h, const int8_t* spins, const float* weights, int N,
+                        float* workspace, float* grad, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (N < 0 || (N > 0 && (!spins || !weights || !workspace)) || !grad)
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "backward: null argument");
+    else if (N > 0) {
+        cudaError_t e = launch_backward(h, spins, weights, N, workspace, grad, (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "logpsi_backward");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+} // extern "C"

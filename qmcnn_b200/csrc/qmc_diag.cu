@@ -1,0 +1,84 @@
+// qmc_diag.cu - roofline denominators the driver's MEASURED_PEAKS.json does not
+// carry: FP32 FMA and MUFU (ex2) issue peaks, measured on the device with
+// unrolled register-only loops.  Diagnostics only; not on the hot path.
+#include <cuda_runtime.h>
+#include "qmcnn_b200.h"
+
+namespace {
+
+template <int ILP>
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <int ILP>
+__global__ void __launch_bounds__(256) k_mufu_peak(float* out, int iters) {
+    float x[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = threadIdx.x * 1e-3f + i * 0.01f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+} // namespace
+
+extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) return QMC_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    float* d = nullptr;
+    cudaMalloc(&d, 16);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    constexpr int ILP = 8;
+    const int grid = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double best_f = 0, best_m = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        float ms = 0;
+        cudaEventRecord(e0);
+        k_fma_peak<ILP><<<grid, threads>>>(d, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * grid * threads * (double)iters * 8 * ILP;
+        if (ms > 0 && flop / (ms * 1e-3) * 1e-12 > best_f) best_f = flop / (ms * 1e-3) * 1e-12;
+        cudaEventRecord(e0);
+        k_mufu_peak<ILP><<<grid, threads>>>(d, iters / 4);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = (double)grid * threads * (iters / 4) * 8.0 * ILP;
+        if (ms > 0 && ops / (ms * 1e-3) * 1e-9 > best_m) best_m = ops / (ms * 1e-3) * 1e-9;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    cudaSetDevice(prev);
+    if (fp32_tflops) *fp32_tflops = best_f;
+    if (mufu_gops) *mufu_gops = best_m;
+    return e == cudaSuccess ? QMC_OK : QMC_ERR_CUDA;
+}

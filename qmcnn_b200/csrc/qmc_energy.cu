@@ -1,0 +1,150 @@
+// qmc_energy.cu - K3: local energies, every connected configuration of every
+// sample as a receptive-field delta.
+// Replaces ising_energy (mcmc_tf.py:59-90) and heisenberg_energy
+// (mcmc_tf.py:93-141) including all_windows / interactions
+// (helpers.py:149-195): instead of gathering N*L^2 windows of (2K-1)^2 spins
+// and running the full network on each, a warp evaluates each flipped
+// configuration incrementally against the sample's activation cache (filled by
+// K1) and accumulates exp(log_pop) in registers.
+#include "qmc_host.h"
+
+namespace qmc {
+
+constexpr int kEnergyChunks = 8;   // site chunks per sample (warp tasks = N * chunks)
+
+__global__ void __launch_bounds__(512)
+k_energy(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
+         const float* __restrict__ cache_all, int hamiltonian, float2* __restrict__ partial,
+         int nchunks, EvalPlan pl, bool allow_tiled) {
+    extern __shared__ float4 smem4[];
+    float* sp = reinterpret_cast<float*>(smem4);
+    load_params_to_smem(m, params, sp);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    char* wmem = reinterpret_cast<char*>(sp + m.smem_param_floats) + (size_t)warp * pl.per_warp_bytes;
+    float* buf0 = reinterpret_cast<float*>(wmem);
+    float* buf1 = buf0 + pl.buf_floats[0];
+    float* newf = buf1 + pl.buf_floats[1];
+    int8_t* spins_s = reinterpret_cast<int8_t*>(newf + pl.newf_floats);
+
+    const int n = m.n, Ly = m.Ly, Lx = m.Lx;
+    const int cs = (n + nchunks - 1) / nchunks;
+    const long long ntasks = (long long)N * nchunks;
+    const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
+    int loaded = -1;
+    for (long long task = slot; task < ntasks; task += nslots) {
+        const int s = (int)(task / nchunks), chunk = (int)(task - (long long)s * nchunks);
+        if (s != loaded) {
+            __syncwarp();
+            for (int i = lane; i < n; i += kWarp) spins_s[i] = spins[(size_t)s * n + i];
+            __syncwarp();
+            loaded = s;
+        }
+        const float* cache = cache_all + (size_t)s * m.cache_floats;
+        float are = 0.f, aim = 0.f;
+        const int i1 = min(n, (chunk + 1) * cs);
+        for (int i = chunk * cs; i < i1; ++i) {
+            Region reg;
+            float dre, dim, sn, cn;
+            if (hamiltonian == QMC_HAMILTONIAN_TFIM) {
+                const FlipBox box = make_box(m, 1, i, -1);
+                warp_eval_flip<true>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride, box,
+                                     lane, allow_tiled, reg, dre, dim);
+                const float amp = expf(dre);
+                sincosf(dim, &sn, &cn);
+                are += amp * cn;               // exp(log_pop), mcmc_tf.py:88
+                aim += amp * sn;
+            } else {
+                const int y = i / Lx, x = i - y * Lx;
+                for (int d = 0; d < 2; ++d) {
+                    const int j = d == 0 ? (y + 1 == Ly ? 0 : y + 1) * Lx + x
+                                         : y * Lx + (x + 1 == Lx ? 0 : x + 1);
+                    if (j == i) { are += 1.f; continue; }          // L == 1 along d: s_i s_i = 1
+                    if (spins_s[i] == spins_s[j]) { are += 1.f; continue; }  // -(1-1) exp + 1
+                    const FlipBox box = make_box(m, 2, i, j);
+                    warp_eval_flip<true>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride,
+                                         box, lane, allow_tiled, reg, dre, dim);
+                    const float amp = expf(dre);
+                    sincosf(dim, &sn, &cn);
+                    are += -2.f * amp * cn - 1.f;      // -(1-(-1)) exp(log_pop) + (-1), mcmc_tf.py:138
+                    aim += -2.f * amp * sn;
+                }
+            }
+        }
+        if (lane == 0) partial[(size_t)s * nchunks + chunk] = make_float2(are, aim);
+    }
+}
+
+// one thread per sample: ordered chunk sum, diagonal term, per-spin normalisation
+__global__ void k_energy_finish(DevModel m, const int8_t* __restrict__ spins, int N, int hamiltonian,
+                                float field_h, const float2* __restrict__ partial, int nchunks,
+                                float2* __restrict__ e_loc, double* __restrict__ moments) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double mre = 0, mim = 0, msq = 0, cnt = 0;
+    if (s < N) {
+        float re = 0.f, im = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            const float2 v = partial[(size_t)s * nchunks + c];
+            re += v.x; im += v.y;
+        }
+        if (hamiltonian == QMC_HAMILTONIAN_TFIM) {
+            int aligned = 0;                        // helpers.py:171-195 interactions, summed
+            const int8_t* sp = spins + (size_t)s * m.n;
+            for (int y = 0; y < m.Ly; ++y)
+                for (int x = 0; x < m.Lx; ++x) {
+                    const int c = sp[y * m.Lx + x];
+                    aligned += c * sp[(y + 1 == m.Ly ? 0 : y + 1) * m.Lx + x];
+                    aligned += c * sp[y * m.Lx + (x + 1 == m.Lx ? 0 : x + 1)];
+                }
+            re = -field_h * re - (float)aligned;    // mcmc_tf.py:88-89
+            im = -field_h * im;
+        }
+        re /= (float)m.n; im /= (float)m.n;         // mcmc_tf.py:90 / 141
+        e_loc[s] = make_float2(re, im);
+        mre = re; mim = im; msq = (double)re * re + (double)im * im; cnt = 1;
+    }
+    if (moments) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mre += __shfl_xor_sync(0xffffffffu, mre, o);
+            mim += __shfl_xor_sync(0xffffffffu, mim, o);
+            msq += __shfl_xor_sync(0xffffffffu, msq, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if ((threadIdx.x & 31) == 0 && cnt > 0) {
+            atomicAdd(moments + 0, cnt); atomicAdd(moments + 1, mre);
+            atomicAdd(moments + 2, mim); atomicAdd(moments + 3, msq);
+        }
+    }
+}
+
+int energy_chunks(const qmc_handle* h) { return h->m.n < kEnergyChunks ? h->m.n : kEnergyChunks; }
+
+cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins,
+                          int N, float* workspace, float* e_loc, double* moments, cudaStream_t st,
+                          std::string& err) {
+    const DevModel& m = h->m;
+    const bool heis = hamiltonian == QMC_HAMILTONIAN_HEISENBERG;
+    const int h0 = heis ? 2 : 1;
+    if (!box_supported(m, h0, h0)) {
+        err = "local_energy: receptive field (+1 for Heisenberg bonds) exceeds the lattice";
+        return cudaErrorInvalidValue;
+    }
+    float* cache = workspace;
+    const int nchunks = energy_chunks(h);
+    float2* partial = reinterpret_cast<float2*>(workspace + (size_t)N * m.cache_floats);
+    cudaError_t e = launch_forward(h, spins, N, cache, nullptr, nullptr, st, err);
+    if (e != cudaSuccess) return e;
+    EvalPlan pl = eval_plan(m, h0, h0, true);
+    WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, (long long)N * nchunks);
+    if (!g.ok) { err = "local_energy: model does not fit in shared memory"; return cudaErrorInvalidValue; }
+    e = cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    k_energy<<<g.grid, g.warps * 32, g.smem, st>>>(m, h->d_params, spins, N, cache, hamiltonian, partial,
+                                                  nchunks, pl, h->allow_tiled);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_energy_finish<<<(N + 127) / 128, 128, 0, st>>>(m, spins, N, hamiltonian, field_h, partial, nchunks,
+                                                    reinterpret_cast<float2*>(e_loc), moments);
+    return cudaGetLastError();
+}
+
+} // namespace qmc

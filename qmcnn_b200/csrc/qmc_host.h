@@ -1,0 +1,122 @@
+// qmc_host.h - host-side handle, launch-geometry helpers and launcher
+// declarations shared by the translation units of libqmcnn_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "qmc_device.cuh"
+
+struct qmc_handle {
+    int device = 0;
+    qmc_model_desc desc{};
+    qmc::DevModel m{};
+    float* d_params = nullptr;
+    std::string err;
+    int num_sms = 0;
+    size_t max_smem = 0;   // opt-in dynamic shared memory per CTA
+    bool allow_tiled = true;  // QMC_FORCE_GENERIC=1 disables the specialised conv instances
+};
+
+namespace qmc {
+
+inline int round4(int v) { return (v + 3) & ~3; }
+
+// shared-memory plan of warp_eval_flip for boxes up to h0max x w0max
+struct EvalPlan {
+    int buf_floats[2];   // ping-pong tile buffers
+    int newf_floats;     // new per-site factors over the last region (x2 when Im is needed)
+    int nfstride;
+    int spins_bytes;     // per-warp lattice copy
+    int staging_floats;  // new hidden activations of all regions (global scratch per warp)
+    size_t per_warp_bytes;
+};
+
+inline EvalPlan eval_plan(const DevModel& m, int h0max, int w0max, bool need_im) {
+    EvalPlan pl{};
+    const int p = m.p;
+    int rh = h0max + 2 * p, rw = w0max + 2 * p;
+    if (rh > m.Ly) rh = m.Ly;
+    if (rw > m.Lx) rw = m.Lx;
+    int bf[2] = {(rh + 2 * p) * (rw + 2 * p), 0};
+    int stg = 0;
+    for (int l = 0; l < m.D; ++l) {
+        const LayerInfo& L = m.layer[l];
+        int& dst = bf[(l + 1) & 1];
+        if (l == m.D - 1) {
+            dst = dst > rh * rw * L.coutp ? dst : rh * rw * L.coutp;
+        } else {
+            const int t = (rh + 4 * p) * (rw + 4 * p) * L.coutp;
+            dst = dst > t ? dst : t;
+            stg += L.coutp * rh * rw;
+            rh += 2 * p; rw += 2 * p;
+        }
+    }
+    pl.buf_floats[0] = round4(bf[0]);
+    pl.buf_floats[1] = round4(bf[1]);
+    pl.nfstride = round4(rh * rw);
+    pl.newf_floats = pl.nfstride * (need_im ? 2 : 1);
+    pl.spins_bytes = (m.n + 15) & ~15;
+    pl.staging_floats = round4(stg);
+    pl.per_warp_bytes = (size_t)(pl.buf_floats[0] + pl.buf_floats[1] + pl.newf_floats) * 4 + pl.spins_bytes;
+    return pl;
+}
+
+// does a box of h0 x w0 flipped sites fit the incremental evaluator?
+inline bool box_supported(const DevModel& m, int h0, int w0) {
+    if (m.D == 1) return true;   // regions clamp to the lattice, spins are re-read by coordinate
+    return h0 + 2 * m.D * m.p <= m.Ly && w0 + 2 * m.D * m.p <= m.Lx;
+}
+
+struct WarpGrid { int grid, warps; size_t smem; bool ok; };
+
+// one CTA per SM, W warps, W chosen to minimise the idle tail over `units` warp tasks
+inline WarpGrid pick_warp_grid(const qmc_handle* h, size_t per_warp_bytes, size_t cta_bytes,
+                               long long units, int max_warps = 16) {
+    WarpGrid g{0, 0, 0, false};
+    const size_t param_bytes = (size_t)h->m.smem_param_floats * 4 + cta_bytes;
+    if (param_bytes + per_warp_bytes > h->max_smem) return g;
+    int wmax = (int)((h->max_smem - param_bytes) / per_warp_bytes);
+    if (wmax > max_warps) wmax = max_warps;
+    int best = wmax;
+    double best_eff = -1;
+    const int wmin = wmax > 2 ? (wmax + 1) / 2 : 1;
+    for (int w = wmax; w >= wmin; --w) {
+        const long long slots = (long long)h->num_sms * w;
+        const long long waves = (units + slots - 1) / slots;
+        const double eff = (double)units / (double)(waves * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+    }
+    g.warps = best;
+    long long ctas = (units + best - 1) / best;
+    g.grid = (int)(ctas < h->num_sms ? ctas : h->num_sms);
+    if (g.grid < 1) g.grid = 1;
+    g.smem = param_bytes + per_warp_bytes * best;
+    g.ok = true;
+    return g;
+}
+
+struct SweepArgs {
+    int8_t* spins; float* cache; float* staging;
+    int S, num_flips;
+    long long step0, n_steps;
+    const int32_t* flip_pos; const float* uniforms;
+    unsigned long long seed; long long chain_id0;
+    long long therm_its, its_per_sample;
+    int8_t* samples; uint8_t* accept_trace; float* logratio_trace;
+    unsigned long long* n_accept;
+};
+
+// launchers (each in its own .cu); return cudaError_t of the launch
+cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
+                           float* factors, float* logpsi, cudaStream_t st, std::string& err);
+cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
+cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins,
+                          int N, float* workspace, float* e_loc, double* moments, cudaStream_t st,
+                          std::string& err);
+cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const float* weights, int N,
+                            float* workspace, float* grad, cudaStream_t st, std::string& err);
+
+int sweep_slots(const qmc_handle* h, int S, int num_flips, EvalPlan* plan, WarpGrid* grid);
+int energy_chunks(const qmc_handle* h);
+size_t backward_workspace_floats(const qmc_handle* h, int N);
+
+} // namespace qmc

@@ -1,0 +1,178 @@
+"""Local-energy estimators, VMC loss and optimisation step with the reference's
+names (reference ``mcmc_tf.py:35-194``), backed by the CUDA energy and backward
+kernels.
+
+The reference reads ``K, H, SYSTEM_SHAPE`` from module globals
+(``mcmc_tf.py:15-25``); the same names exist here as module attributes with the
+same defaults and can be overridden per call with keyword arguments.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .helpers import scope_op
+from .models import _stream_ptr
+
+LEARNING_RATE = 3E-3
+K = 5
+SYSTEM_SHAPE = (10, 10)
+H = 1.0
+ENERGY_BATCH_SIZE = 1000
+
+
+def _prep(model, states, system_shape):
+    system_shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
+    states = torch.as_tensor(states, device=model.device)
+    n = int(np.prod(system_shape))
+    states = states.reshape(-1, n)
+    if states.dtype != torch.int8:
+        states = states.to(torch.int8)
+    return states.contiguous(), system_shape, model.handle(system_shape)
+
+
+def _local_energy(model, states, system_shape, hamiltonian, h_field, moments=None):
+    states, system_shape, h = _prep(model, states, system_shape)
+    N = states.shape[0]
+    out = torch.empty(N, dtype=torch.complex64, device=model.device)
+    if N == 0:
+        return out
+    lib = _lib.load()
+    ws = torch.empty(lib.qmc_energy_workspace_floats(h.ptr, N), dtype=torch.float32, device=model.device)
+    _lib.check(h.ptr, lib.qmc_local_energy(
+        h.ptr, hamiltonian, float(h_field), states.data_ptr(), N, ws.data_ptr(), out.data_ptr(),
+        moments.data_ptr() if moments is not None else None, _stream_ptr(model.device)),
+        "qmc_local_energy")
+    return out
+
+
+@scope_op()
+def ising_energy(model, states, system_shape=None, K=None, H=None, moments=None):
+    """``mcmc_tf.py:59-90``: TFIM local energy PER SPIN, complex64 (N,).
+    ``K`` (the receptive field) is implied by the model and only checked."""
+    if K is not None and K != model.r:
+        raise _lib.QmcError("ising_energy: K=%d differs from the model's receptive field %d" % (K, model.r))
+    return _local_energy(model, states, system_shape, _lib.TFIM,
+                         globals()["H"] if H is None else H, moments)
+
+
+@scope_op()
+def heisenberg_energy(model, states, system_shape=None, K=None, moments=None):
+    """``mcmc_tf.py:93-141``: Marshall-signed AFM Heisenberg local energy per spin."""
+    if K is not None and K != model.r:
+        raise _lib.QmcError("heisenberg_energy: K=%d differs from the model's receptive field %d"
+                            % (K, model.r))
+    return _local_energy(model, states, system_shape, _lib.HEISENBERG, 0.0, moments)
+
+
+@scope_op()
+def batched_op(fn, states, batch_size):
+    """``mcmc_tf.py:144-153``: apply ``fn`` to chunks of ``batch_size`` rows.  The CUDA
+    energy kernel needs no chunking; this keeps the call working (and bounds the
+    workspace) for scripts that use it."""
+    states = torch.as_tensor(states)
+    if states.shape[0] % batch_size:
+        raise _lib.QmcError("batched_op: %d rows are not a multiple of batch_size %d"
+                            % (states.shape[0], batch_size))
+    return torch.cat([fn(states[i:i + batch_size]) for i in range(0, states.shape[0], batch_size)])
+
+
+@scope_op()
+def loss_op(factors, energies):
+    """``mcmc_tf.py:35-56``: Re[<E conj(log psi)> - <E><conj(log psi)>] (real scalar)."""
+    n = factors.shape[0]
+    energies = energies.to(torch.complex64)
+    lpc = torch.conj(factors.reshape(n, -1).sum(1))
+    e_avg = energies.sum() / n
+    return ((energies * lpc).sum() / n - e_avg * lpc.sum() / n).real
+
+
+def logpsi_gradient(model, states, weights, system_shape=None, out=None):
+    """sum_n Re[w_n conj(d log psi_n / d p)] as a flat fp32 vector in ``model.flat`` order.
+    With w_n = (E_n - mean E)/N this is d loss_op / d p (``mcmc_tf.py:172-177``)."""
+    states, system_shape, h = _prep(model, states, system_shape)
+    N = states.shape[0]
+    grad = torch.zeros(model.num_params, dtype=torch.float32, device=model.device) if out is None else out
+    if N == 0:
+        return grad
+    weights = weights.to(torch.complex64).contiguous()
+    lib = _lib.load()
+    ws = torch.empty(lib.qmc_backward_workspace_floats(h.ptr, N), dtype=torch.float32, device=model.device)
+    _lib.check(h.ptr, lib.qmc_logpsi_backward(h.ptr, states.data_ptr(), weights.data_ptr(), N,
+                                              ws.data_ptr(), grad.data_ptr(),
+                                              _stream_ptr(model.device)), "qmc_logpsi_backward")
+    return grad
+
+
+class AdamTF1(object):
+    """``tf.train.AdamOptimizer`` (``mcmc_tf.py:176``), TF-1 update form:
+    lr_t = lr sqrt(1-b2^t)/(1-b1^t);  p -= lr_t m / (sqrt(v) + eps)."""
+
+    def __init__(self, flat, lr=LEARNING_RATE, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.flat, self.lr, self.b1, self.b2, self.eps = flat, lr, beta1, beta2, eps
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self.t = 0
+
+    def step(self, grad):
+        self.t += 1
+        self.m.mul_(self.b1).add_(grad, alpha=1 - self.b1)
+        self.v.mul_(self.b2).addcmul_(grad, grad, value=1 - self.b2)
+        lr_t = self.lr * np.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        self.flat.addcdiv_(self.m, self.v.sqrt().add_(self.eps), value=-lr_t)
+
+
+class OptimizeStep(object):
+    """What ``optimize_op`` returns: ``run()`` does one VMC iteration
+    (``mcmc_tf.py:156-179``): sample, local energies, gradient of ``loss_op``, Adam.
+    Under ``torch.distributed`` (one rank per GPU, chains sharded) the energy
+    moments and the gradient are all-reduced over NCCL - the only collectives."""
+
+    def __init__(self, sampler, model, energy_fn, learning_rate=LEARNING_RATE, group=None):
+        self.sampler, self.model, self.energy_fn = sampler, model, energy_fn
+        self.optimizer = AdamTF1(model.flat, learning_rate)
+        self.group = group
+        self.last_grad = None
+
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def run(self, new_samples=None):
+        import torch.distributed as dist
+        if new_samples is not None:
+            self.sampler.new_samples = bool(new_samples)
+        self.sampler.mcmc_op()
+        samples = self.sampler.samples_int8()
+        energies = self.energy_fn(samples)
+        n_local = energies.shape[0]
+        world = self._world()
+        mom = torch.stack([torch.tensor(float(n_local), device=energies.device, dtype=torch.float64),
+                           energies.real.double().sum(), energies.imag.double().sum()])
+        if world > 1:
+            dist.all_reduce(mom, group=self.group)                 # collective 1: energy moments
+        n_tot = mom[0]
+        e_mean = torch.complex(mom[1] / n_tot, mom[2] / n_tot).to(torch.complex64)
+        weights = (energies - e_mean) / n_tot.to(torch.float32)
+        grad = logpsi_gradient(self.model, samples, weights, self.sampler.system_shape)
+        if world > 1:
+            dist.all_reduce(grad, group=self.group)                # collective 2: gradient
+        self.last_grad = grad
+        self.optimizer.step(grad)
+        return energies
+
+
+@scope_op()
+def optimize_op(sampler, model, energy_fn, learning_rate=LEARNING_RATE, group=None):
+    """``mcmc_tf.py:156-179``. Returns an :class:`OptimizeStep`; ``.run()`` returns the
+    sampled local energies after applying one Adam update."""
+    return OptimizeStep(sampler, model, energy_fn, learning_rate, group)
+
+
+@scope_op()
+def eval_op(sampler, model, energy_fn, batch_size=None):
+    """``mcmc_tf.py:182-194``: energies of a fresh ``mcmc_op`` in batches."""
+    samples = sampler.mcmc_op()
+    bs = ENERGY_BATCH_SIZE if batch_size is None else batch_size
+    if samples.shape[0] % bs:
+        bs = samples.shape[0]
+    return batched_op(energy_fn, samples, bs)

@@ -1,0 +1,139 @@
+"""Wavefunction models with the reference's constructor and ``factors`` call
+signatures (reference ``models.py``), backed by the CUDA forward kernel.
+
+Parameters live in ONE flat fp32 CUDA tensor in the reference's variable
+creation order and HWIO layout; ``model.params[name]`` are views into it
+("filters", "bias_vis", "bias_hid" / "filters_%d", "bias_%d").
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .helpers import scope_op
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _Model(object):
+    SCALE = 1E-2
+
+    def _init_params(self, specs, device, seed):
+        if not torch.cuda.is_available():
+            raise _lib.QmcError("qmcnn_b200 needs a CUDA device (B200); there is no CPU fallback")
+        _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        total = sum(int(np.prod(s)) for _, s in specs)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(seed) if seed is not None else int(np.random.randint(2 ** 31)))
+        self.flat = (torch.randn(total, generator=gen, dtype=torch.float32) * self.SCALE).to(self.device)
+        self.names = [n for n, _ in specs]
+        self.params, o = {}, 0
+        for n, s in specs:
+            size = int(np.prod(s))
+            self.params[n] = self.flat[o:o + size].view(*s)
+            o += size
+        self._handles = {}
+
+    @property
+    def num_params(self):
+        return self.flat.numel()
+
+    def set_flat_params(self, flat):
+        self.flat.copy_(torch.as_tensor(flat, dtype=torch.float32).reshape(-1))
+
+    def handle(self, system_shape):
+        """The library handle for this model on an Ly x Lx lattice, parameters synced."""
+        system_shape = tuple(int(s) for s in system_shape)
+        if len(system_shape) != 2:
+            raise _lib.QmcError("the CUDA path covers 2-D lattices (n_dims == 2)")
+        h = self._handles.get(system_shape)
+        if h is None:
+            h = _lib.Handle(self._kind, self.k, self._channels, system_shape[0], system_shape[1],
+                            self.device.index or 0)
+            assert h.num_params == self.flat.numel()
+            self._handles[system_shape] = h
+        _lib.check(h.ptr, _lib.load().qmc_set_params(h.ptr, self.flat.data_ptr(),
+                                                     _stream_ptr(self.device)), "qmc_set_params")
+        return h
+
+    # ---- forward ------------------------------------------------------------
+    def _halo(self):
+        return (self.r - 1) // 2
+
+    def forward_unpadded(self, spins, system_shape, want_factors=True, want_logpsi=False, cache=None):
+        """K1 on UN-padded int8 spins (N, Ly*Lx). Returns (factors, logpsi, cache)."""
+        h = self.handle(system_shape)
+        spins = spins.reshape(-1, h.n)
+        if spins.dtype != torch.int8:
+            spins = spins.to(torch.int8)
+        spins = spins.contiguous()
+        N = spins.shape[0]
+        if cache is None:
+            cache = torch.empty(N * h.cache_floats, dtype=torch.float32, device=self.device)
+        factors = torch.empty((N, h.n), dtype=torch.complex64, device=self.device) if want_factors else None
+        logpsi = torch.empty(N, dtype=torch.complex64, device=self.device) if want_logpsi else None
+        _lib.check(h.ptr, _lib.load().qmc_logpsi_forward(
+            h.ptr, spins.data_ptr(), N, cache.data_ptr(),
+            factors.data_ptr() if want_factors else None,
+            logpsi.data_ptr() if want_logpsi else None, _stream_ptr(self.device)), "qmc_logpsi_forward")
+        return factors, logpsi, cache
+
+    @scope_op("factors")
+    def factors(self, x, check_periodic=True):
+        """``models.py:31-67`` / ``95-131``.
+
+        x : (N,) + padded lattice, +-1, wrap-padded by (r-1)//2 as the reference's
+        callers do.  Returns complex64 (N,) + system_shape.  The CUDA path
+        evaluates the periodic lattice directly, so ``x`` must be a periodic
+        image (checked unless ``check_periodic=False``).
+        """
+        x = torch.as_tensor(x, device=self.device)
+        halo = self._halo()
+        shape = tuple(int(s) - 2 * halo for s in x.shape[1:])
+        if len(shape) != 2 or min(shape) < 1:
+            raise _lib.QmcError("factors: expected (N, Ly+r-1, Lx+r-1) wrap-padded input")
+        inner = x[:, halo:halo + shape[0], halo:halo + shape[1]]
+        if check_periodic and halo:
+            iy = torch.arange(-halo, shape[0] + halo, device=x.device) % shape[0]
+            ix = torch.arange(-halo, shape[1] + halo, device=x.device) % shape[1]
+            if not torch.equal(inner[:, iy][:, :, ix], x):
+                raise _lib.QmcError("factors: input is not a periodic (wrap-padded) image; the CUDA "
+                                    "path evaluates periodic lattices only")
+        f, _, _ = self.forward_unpadded(inner.reshape(x.shape[0], -1), shape)
+        return f.view((x.shape[0],) + shape)
+
+    def log_psi(self, spins, system_shape):
+        """log psi of UN-padded states (N, Ly*Lx) -> complex64 (N,)."""
+        return self.forward_unpadded(spins, system_shape, want_factors=False, want_logpsi=True)[1]
+
+
+class CRBM(_Model):
+    """Convolutional marginalised RBM, ``models.py:6-67``."""
+
+    def __init__(self, k, pad_size, alpha, n_dims, device=None, seed=None):
+        if n_dims != 2:
+            raise _lib.QmcError("the CUDA path covers n_dims == 2")
+        self.k, self.pad_size, self.alpha, self.n_dims = k, pad_size, alpha, n_dims
+        self.r = k
+        self._kind, self._channels = _lib.MODEL_CRBM, [2 * alpha]
+        self._init_params([("filters", (k, k, 1, 2 * alpha)), ("bias_vis", (2,)),
+                           ("bias_hid", (2 * alpha,))], device, seed)
+
+
+class DCRBM(_Model):
+    """Deep convolutional marginalised RBM, ``models.py:70-131``."""
+
+    def __init__(self, k, layers, n_dims, device=None, seed=None):
+        if n_dims != 2:
+            raise _lib.QmcError("the CUDA path covers n_dims == 2")
+        self.k, self.layers, self.n_dims = k, list(layers), n_dims
+        self.r = len(self.layers) * (k - 1) + 1
+        self._kind, self._channels = _lib.MODEL_DCRBM, list(layers)
+        chans = [1] + self.layers
+        specs = []
+        for l, (cin, cout) in enumerate(zip(chans, chans[1:])):
+            specs += [("filters_%d" % l, (k, k, cin, cout)), ("bias_%d" % l, (cout,))]
+        self._init_params(specs, device, seed)

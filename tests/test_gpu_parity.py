@@ -1,0 +1,366 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+identical inputs.  Tolerances are the ones BASELINE.json's north_star states:
+log psi and local energies within 1e-5 relative (fp32); flip indices and accept
+decisions bit-exact except where |log-ratio - log u| is inside the fp32 noise
+band; gradients within 1e-4 of the gradient scale (fp32 reduction over N*L^2
+terms - not stated by north_star, stated here)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.philox import sweep_randoms
+
+pytestmark = pytest.mark.gpu
+
+LOGPSI_RTOL = 1e-5
+ELOC_RTOL = 1e-5
+TIE_BAND = 1e-5      # |2 Re log-ratio - log u| below which a differing accept is a tie
+
+
+def _q():
+    import qmcnn_b200
+    return qmcnn_b200
+
+
+CASES = [
+    # name, kind, (Ly, Lx), kwargs
+    ("C1-crbm-6x6", "crbm", (6, 6), dict(k=5, alpha=4)),
+    ("crbm-k3-5x7", "crbm", (5, 7), dict(k=3, alpha=3)),
+    ("C2-dcrbm-10x10", "dcrbm", (10, 10), dict(k=3, layers=[8, 8, 8])),
+    ("dcrbm-odd-channels-9x8", "dcrbm", (9, 8), dict(k=3, layers=[3, 5, 6])),
+    ("dcrbm-16-13x14", "dcrbm", (13, 14), dict(k=3, layers=[16, 16, 16, 8])),
+    ("dcrbm-k5-12x12", "dcrbm", (12, 12), dict(k=5, layers=[4, 2])),
+]
+
+
+@pytest.mark.parametrize("name,kind,shape,kw", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("scale", [1e-2, 1e-1])
+def test_forward_matches_oracle(name, kind, shape, kw, scale):
+    from gpu_util import make_pair, rand_states, padded, rel_err
+    gm, om = make_pair(kind, shape[0], scale, 1234, **kw)
+    rng = np.random.default_rng(5)
+    s = rand_states(rng, 7, shape)
+    xp = padded(om, s, shape)
+    want32 = om.factors(xp)
+    want64 = om.astype(np.float64).factors(xp)
+    got = gm.factors(torch.as_tensor(xp)).cpu().numpy()
+    assert got.shape == want32.shape and got.dtype == np.complex64
+    # per-site factors: absolute error at the fp32 rounding level of the values
+    assert np.abs(got - want64).max() < 2e-6 * max(1.0, np.abs(want64).max())
+    lp = gm.log_psi(torch.as_tensor(s), shape).cpu().numpy()
+    lp64 = want64.reshape(7, -1).sum(1)
+    assert rel_err(lp, lp64) < LOGPSI_RTOL
+    assert rel_err(lp, want32.reshape(7, -1).sum(1)) < LOGPSI_RTOL
+
+
+def test_forward_rejects_non_periodic_input():
+    from gpu_util import make_pair
+    gm, om = make_pair("crbm", 6, 1e-2, 1, k=3, alpha=2)
+    x = torch.ones((2, 8, 8), dtype=torch.int32)
+    x[0, 0, 0] = -1
+    with pytest.raises(_q().QmcError):
+        gm.factors(x)
+
+
+def test_forward_empty_and_single():
+    from gpu_util import make_pair, rand_states
+    gm, om = make_pair("dcrbm", 6, 1e-1, 2, layers=[4, 2])
+    out = gm.log_psi(torch.zeros((0, 36), dtype=torch.int8), (6, 6))
+    assert out.shape == (0,)
+    s = rand_states(np.random.default_rng(0), 1, (6, 6))
+    assert gm.log_psi(torch.as_tensor(s), (6, 6)).shape == (1,)
+
+
+def test_specialised_conv_is_bit_identical_to_generic():
+    """The register-tiled instances must round exactly like the generic loop."""
+    from gpu_util import make_pair, rand_states
+    shape = (13, 14)
+    s = torch.as_tensor(rand_states(np.random.default_rng(3), 5, shape))
+    outs = []
+    for force in ("0", "1"):
+        os.environ["QMC_FORCE_GENERIC"] = force
+        try:
+            gm, _ = make_pair("dcrbm", 13, 1e-1, 77, layers=[16, 16, 16, 8])
+            outs.append(gm.forward_unpadded(s, shape)[0].cpu().numpy())
+        finally:
+            os.environ.pop("QMC_FORCE_GENERIC", None)
+    assert np.array_equal(outs[0].view(np.float32), outs[1].view(np.float32))
+
+
+# ----------------------------------------------------------------------------- sweep
+def _lockstep(gm, om, shape, S, n_steps, num_flips, seed, sweepfactor=None):
+    """Run the CUDA sweep with traces on fed-in randoms and replay the oracle in
+    lock-step; on a differing decision check it is a tie and resync the oracle."""
+    q = _q()
+    r = om.r
+
+    class GS(q.Sampler):
+        MAX_NUM_SAMPLERS = 10 ** 9
+
+    class OS(oracle.Sampler):
+        MAX_NUM_SAMPLERS = 10 ** 9
+    if sweepfactor is not None:
+        GS.SWEEPFACTOR = OS.SWEEPFACTOR = sweepfactor
+    rng = np.random.default_rng(seed)
+    n = shape[0] * shape[1]
+    init = (rng.integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+    pos = rng.integers(0, n, (n_steps, S, num_flips)).astype(np.int32)
+    if num_flips == 2:
+        pos[1, 0] = pos[1, 0, 0]          # an identity double flip
+    u = rng.random((n_steps, S)).astype(np.float32)
+    gs = GS(gm, shape, r, S, num_flips)
+    gs.feed(init, pos, u)
+    gs.mcmc_op(n_its=n_steps, trace=True)
+    acc = gs.accept_trace.cpu().numpy().astype(bool)
+    lr = gs.logratio_trace.cpu().numpy()
+    os_ = OS(om, shape, r, S, num_flips)
+    os_.mcmc_reset(init, pos, u)
+    ties, max_dlr = 0, 0.0
+    for i in range(n_steps):
+        os_.mcmc_step(i)
+        olr = os_.last_log_ratio.real
+        max_dlr = max(max_dlr, float(np.abs(olr - lr[i]).max()))
+        diff = os_.last_mask != acc[i]
+        if diff.any():
+            for c in np.nonzero(diff)[0]:
+                gap = abs(2.0 * float(olr[c]) - np.log(max(float(u[i, c]), 1e-45)))
+                assert gap < TIE_BAND, "step %d chain %d: decisions differ outside the tie band (%g)" % (i, c, gap)
+                ties += 1
+                # resync the oracle to the GPU's decision
+                cur = os_.unpadded_current().copy()
+                for f in range(num_flips):
+                    cur[c, pos[i, c, f]] *= -1
+                halo = (r - 1) // 2
+                os_.current_samples[c] = oracle.pad(cur[c].reshape((1,) + tuple(shape)), shape,
+                                                    [halo, halo]).reshape(-1)
+                os_.current_factors[c] = om.factors(
+                    os_.current_samples[c].reshape((1,) + os_.padded_shape)).reshape(-1)
+    assert np.array_equal(gs.spins.cpu().numpy().astype(np.int32), os_.unpadded_current())
+    return gs, os_, ties, max_dlr, acc
+
+
+@pytest.mark.parametrize("scale", [1e-2, 3e-1])
+def test_sweep_lockstep_c1_crbm(scale):
+    """Config C1 (6x6 TFIM CRBM(5,2,4,2), 64 chains): accept decisions bit-exact."""
+    from gpu_util import make_pair
+    gm, om = make_pair("crbm", 6, scale, 1234, k=5, alpha=4)
+    gs, os_, ties, max_dlr, acc = _lockstep(gm, om, (6, 6), 64, 400, 1, seed=11)
+    assert max_dlr < 2e-5
+    assert ties <= 2
+    if scale > 0.1:
+        assert 0.05 < acc.mean() < 0.98      # a non-trivial acceptance rate was exercised
+
+
+@pytest.mark.parametrize("layers,shape", [([8, 8, 8], (10, 10)), ([16, 16, 8], (9, 11)), ([3, 5, 6], (8, 7))])
+def test_sweep_lockstep_dcrbm(layers, shape):
+    from gpu_util import make_pair
+    gm, om = make_pair("dcrbm", shape[0], 2e-1, 99, layers=layers)
+    gs, os_, ties, max_dlr, acc = _lockstep(gm, om, shape, 24, 250, 1, seed=12)
+    assert max_dlr < 2e-5 and ties <= 2
+    assert 0.02 < acc.mean() < 0.999
+
+
+def test_sweep_lockstep_two_flips_crbm():
+    """num_flips = 2 (the Heisenberg sampler of mcmc_tf.py:205-209) incl. the identity proposal."""
+    from gpu_util import make_pair
+    gm, om = make_pair("crbm", 10, 3e-1, 5, k=5, alpha=4)
+    gs, os_, ties, max_dlr, acc = _lockstep(gm, om, (10, 10), 32, 200, 2, seed=13)
+    assert acc[1, 0]                       # identity proposal always accepted
+    assert max_dlr < 2e-5 and ties <= 2
+
+
+def test_sweep_sample_writeout_order():
+    """samples_per_sampler > 1: rows j*S + chain, written after the update (sampler.py:135-152,176-177)."""
+    from gpu_util import make_pair
+    q = _q()
+    gm, om = make_pair("crbm", 4, 3e-1, 8, k=3, alpha=2)
+
+    class GS(q.Sampler):
+        MAX_NUM_SAMPLERS, SWEEPFACTOR, THERMFACTOR = 5, 1, 1
+
+    class OS(oracle.Sampler):
+        MAX_NUM_SAMPLERS, SWEEPFACTOR, THERMFACTOR = 5, 1, 1
+    gs, os_ = GS(gm, (4, 4), 3, 15, 1), OS(om, (4, 4), 3, 15, 1)
+    assert (gs.num_samplers, gs.samples_per_sampler, gs.therm_its, gs.sample_its) == \
+        (os_.num_samplers, os_.samples_per_sampler, os_.therm_its, os_.sample_its) == (5, 3, 48, 81)
+    rng = np.random.default_rng(4)
+    init = (rng.integers(0, 2, (5, 4, 4)) * 2 - 1).astype(np.int32)
+    pos = rng.integers(0, 16, (81, 5, 1)).astype(np.int32)
+    u = rng.random((81, 5)).astype(np.float32)
+    gs.feed(init, pos, u)
+    got = gs.mcmc_op().cpu().numpy()
+    want = os_.mcmc_op(init, pos, u)
+    assert got.shape == (15, 16) and got.dtype == np.int32
+    assert np.array_equal(got, want)
+    assert np.array_equal(gs.current_samples_var.cpu().numpy(), os_.current_samples)
+    assert np.abs(gs.current_factors_var.cpu().numpy() - os_.current_factors).max() < 1e-5
+
+
+def test_sweep_philox_equals_fed_randoms():
+    """In-kernel Philox-4x32-10 == the same stream generated by oracle/philox.py and fed in."""
+    from gpu_util import make_pair
+    q = _q()
+    gm, om = make_pair("dcrbm", 8, 2e-1, 3, layers=[4, 4])
+    S, n_steps, seed, cid0 = 40, 300, 0xDEADBEEFCAFE, 1000
+
+    class GS(q.Sampler):
+        MAX_NUM_SAMPLERS = 10 ** 9
+    init = (np.random.default_rng(1).integers(0, 2, (S, 8, 8)) * 2 - 1).astype(np.int32)
+    a = GS(gm, (8, 8), 5, S, 1, seed=seed, chain_id0=cid0)
+    a.feed(initial_states=init)
+    a.mcmc_op(n_its=n_steps, trace=True)
+    pos, u = sweep_randoms(seed, cid0 + np.arange(S), 0, n_steps, 1, 64)
+    b = GS(gm, (8, 8), 5, S, 1)
+    b.feed(init, pos, u)
+    b.mcmc_op(n_its=n_steps, trace=True)
+    assert torch.equal(a.accept_trace, b.accept_trace)
+    assert torch.equal(a.logratio_trace, b.logratio_trace)
+    assert torch.equal(a.spins, b.spins)
+    assert a.acceptance_count == int(a.accept_trace.sum().item())
+
+
+def test_incremental_cache_equals_full_forward_after_many_flips():
+    """After any flip history the incrementally maintained cache must equal a fresh full
+    forward bit for bit: continue one more step from (a) the incremental cache and (b) a
+    refreshed cache and compare the log-ratios exactly."""
+    from gpu_util import make_pair
+    q = _q()
+    gm, om = make_pair("dcrbm", 12, 3e-1, 21, layers=[16, 16, 8])
+
+    class GS(q.Sampler):
+        MAX_NUM_SAMPLERS = 10 ** 9
+    S = 64
+    a = GS(gm, (12, 12), 7, S, 1, seed=5)
+    a.mcmc_op(n_its=2000)
+    spins = a.spins.clone()
+    a._sweep(10 ** 6, 1, trace=True)             # continues on the incremental cache
+    lr_inc = a.logratio_trace.clone()
+    b = GS(gm, (12, 12), 7, S, 1, seed=5)
+    b.feed(initial_states=spins.cpu().numpy())
+    b.mcmc_reset()                                # fresh full forward
+    b._sweep(10 ** 6, 1, trace=True)
+    assert torch.equal(lr_inc, b.logratio_trace)
+    assert a.acceptance_count > 0
+
+
+# ----------------------------------------------------------------------------- energy
+@pytest.mark.parametrize("name,kind,shape,kw", CASES[:5], ids=[c[0] for c in CASES[:5]])
+@pytest.mark.parametrize("scale", [1e-2, 1e-1])
+def test_ising_energy_matches_oracle(name, kind, shape, kw, scale):
+    from gpu_util import make_pair, rand_states, rel_err
+    q = _q()
+    gm, om = make_pair(kind, shape[0], scale, 4321, **kw)
+    s = rand_states(np.random.default_rng(6), 6, shape)
+    got = q.ising_energy(gm, torch.as_tensor(s), system_shape=shape, H=3.0).cpu().numpy()
+    want64 = oracle.ising_energy(om.astype(np.float64), s, shape, om.r, H=3.0)
+    want32 = oracle.ising_energy(om, s, shape, om.r, H=3.0)
+    assert got.dtype == np.complex64 and got.shape == (6,)
+    assert rel_err(got, want64) < ELOC_RTOL
+    assert rel_err(got, want32) < 2 * ELOC_RTOL
+
+
+@pytest.mark.parametrize("name,kind,shape,kw", [CASES[0][:2] + ((10, 10), CASES[0][3]), CASES[2], CASES[3]],
+                         ids=["C4-crbm-10x10", "dcrbm-10x10", "dcrbm-odd-9x8"])
+def test_heisenberg_energy_matches_oracle(name, kind, shape, kw):
+    from gpu_util import make_pair, rand_states, rel_err
+    q = _q()
+    gm, om = make_pair(kind, shape[0], 1e-1, 999, **kw)
+    s = rand_states(np.random.default_rng(7), 5, shape)
+    got = q.heisenberg_energy(gm, torch.as_tensor(s), system_shape=shape).cpu().numpy()
+    want64 = oracle.heisenberg_energy(om.astype(np.float64), s, shape, om.r)
+    assert rel_err(got, want64) < ELOC_RTOL
+
+
+def test_energy_moments_and_batched_op():
+    from gpu_util import make_pair, rand_states
+    q = _q()
+    gm, om = make_pair("crbm", 6, 1e-1, 1, k=3, alpha=2)
+    s = torch.as_tensor(rand_states(np.random.default_rng(8), 12, (6, 6)))
+    mom = torch.zeros(4, dtype=torch.float64, device="cuda")
+    e = q.ising_energy(gm, s, system_shape=(6, 6), H=1.0, moments=mom)
+    m = mom.cpu().numpy()
+    ec = e.cpu().numpy().astype(np.complex128)
+    assert m[0] == 12 and abs(m[1] - ec.real.sum()) < 1e-9 and abs(m[3] - (np.abs(ec) ** 2).sum()) < 1e-9
+    eb = q.batched_op(lambda x: q.ising_energy(gm, x, system_shape=(6, 6), H=1.0), s, 4)
+    assert torch.equal(e, eb)
+    with pytest.raises(q.QmcError):
+        q.batched_op(lambda x: x, s, 5)
+
+
+def test_energy_rejects_lattice_smaller_than_receptive_field():
+    from gpu_util import make_pair
+    q = _q()
+    gm, om = make_pair("dcrbm", 6, 1e-1, 1, layers=[4, 4, 4, 2])      # r = 9 > 6
+    with pytest.raises(q.QmcError):
+        q.ising_energy(gm, torch.ones((2, 36), dtype=torch.int8), system_shape=(6, 6))
+
+
+# ----------------------------------------------------------------------------- gradient
+@pytest.mark.parametrize("name,kind,shape,kw", CASES[:4], ids=[c[0] for c in CASES[:4]])
+def test_gradient_matches_autograd_oracle(name, kind, shape, kw):
+    from gpu_util import make_pair, rand_states, padded
+    q = _q()
+    gm, om = make_pair(kind, shape[0], 1e-1, 31, **kw)
+    rng = np.random.default_rng(9)
+    N = 9
+    s = rand_states(rng, N, shape)
+    e = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    want, loss = oracle.vmc_gradient(om.astype(np.float64), padded(om, s, shape), e)
+    w = torch.as_tensor((e - e.mean()) / N, device="cuda")
+    got = q.logpsi_gradient(gm, torch.as_tensor(s), w, system_shape=shape).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-4 * np.abs(want).max()
+    # loss_op itself
+    f = gm.factors(torch.as_tensor(padded(om, s, shape)))
+    assert abs(float(q.loss_op(f, torch.as_tensor(e, device="cuda"))) - loss) < 1e-5 * max(1.0, abs(loss))
+
+
+def test_adam_matches_tf1_form():
+    q = _q()
+    flat = torch.tensor([1.0, -2.0], device="cuda")
+    opt = q.AdamTF1(flat, lr=0.1)
+    p = np.array([1.0, -2.0]); m = v = np.zeros(2)
+    for t in range(1, 4):
+        g = np.array([0.5 * t, -0.25])
+        opt.step(torch.as_tensor(g, dtype=torch.float32, device="cuda"))
+        p, m, v = oracle.adam_tf1_step(p, g, m, v, t, lr=0.1)
+    assert np.allclose(flat.cpu().numpy(), p, rtol=1e-5)
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_c3_properties():
+    """BASELINE C3 shapes (20x20, DCRBM k3 [16]*5+[8]): size-independent properties."""
+    from gpu_util import make_pair, rand_states
+    q = _q()
+    shape, layers = (20, 20), [16, 16, 16, 16, 16, 8]
+    gm, om = make_pair("dcrbm", 20, 1e-1, 1237, layers=layers)
+    rng = np.random.default_rng(2)
+    s = rand_states(rng, 16, shape)
+    lp = gm.log_psi(torch.as_tensor(s), shape).cpu().numpy()
+    # translation invariance of log psi and of the local energy
+    sh = np.roll(s.reshape(-1, 20, 20), (3, -7), (1, 2)).reshape(16, -1)
+    lp2 = gm.log_psi(torch.as_tensor(sh), shape).cpu().numpy()
+    assert np.abs(lp - lp2).max() < 1e-5 * np.abs(lp).max()
+    e1 = q.ising_energy(gm, torch.as_tensor(s), system_shape=shape, H=1.0).cpu().numpy()
+    e2 = q.ising_energy(gm, torch.as_tensor(sh), system_shape=shape, H=1.0).cpu().numpy()
+    assert np.abs(e1 - e2).max() < 1e-5 * np.abs(e1).max()
+    # two samples against the oracle at full size
+    want = oracle.ising_energy(om.astype(np.float64), s[:2], shape, om.r, H=1.0)
+    assert np.abs(e1[:2] - want).max() < ELOC_RTOL * np.abs(want).max()
+    # log-ratio of a sweep step equals the difference of two full forwards
+    class GS(q.Sampler):
+        MAX_NUM_SAMPLERS = 10 ** 9
+    smp = GS(gm, shape, 13, 16, 1, seed=3)
+    smp.feed(initial_states=s)
+    smp.mcmc_op(n_its=500)
+    before = smp.spins.clone()
+    lp_before = gm.log_psi(before, shape)
+    smp._sweep(10 ** 7, 1, trace=True)
+    after = smp.spins
+    lp_after = gm.log_psi(after, shape)
+    acc = smp.accept_trace[0].bool()
+    d = (lp_after - lp_before).real[acc].cpu().numpy()
+    assert acc.any()
+    assert np.abs(d - smp.logratio_trace[0][acc].cpu().numpy()).max() < 2e-3   # difference of two ~1e3 totals in fp32
