@@ -101,9 +101,10 @@ int qmc_logpsi_forward(qmc_handle* h, const int8_t* spins, int N, float* cache,
  *   flip_pos [n_steps, S, num_flips] int32 and uniforms [n_steps, S] fp32
  *           (sampler.py:95-100), or BOTH NULL -> in-kernel Philox-4x32-10
  *           keyed (seed; chain_id0 + chain, step) - see oracle/philox.py
- *   samples [sps, S, Ly*Lx] int8 or NULL; sample j = (i-therm_its)/its_per_sample
- *           written after the update when i >= therm_its and
- *           (i-therm_its) % its_per_sample == 0 (sampler.py:135-152)
+ *   samples [n_sample_slots, S, Ly*Lx] int8 or NULL; sample j =
+ *           (i-therm_its)/its_per_sample written after the update when
+ *           i >= therm_its, (i-therm_its) % its_per_sample == 0
+ *           (sampler.py:135-152) and j < n_sample_slots (= samples_per_sampler)
  *   accept_trace [n_steps, S] uint8 or NULL; logratio_trace [n_steps, S] fp32
  *           (Re sum(f' - f)) or NULL; n_accept [1] uint64 (+=) or NULL. */
 int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* workspace,
@@ -111,7 +112,7 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
                          const int32_t* flip_pos, const float* uniforms,
                          uint64_t seed, int64_t chain_id0,
                          int64_t therm_its, int64_t its_per_sample, int8_t* samples,
-                         uint8_t* accept_trace, float* logratio_trace,
+                         int64_t n_sample_slots, uint8_t* accept_trace, float* logratio_trace,
                          unsigned long long* n_accept, void* stream);
 
 /* ising_energy / heisenberg_energy (mcmc_tf.py:59-90, 93-141): local energy

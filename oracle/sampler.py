@@ -81,8 +81,10 @@ class Sampler(object):
         self.flip_positions = np.asarray(flip_positions, np.int32)
         self.accept_sample = np.asarray(accept_sample, np.float32)
 
-    def mcmc_step(self, i):
-        """``sampler.py:104-155``."""
+    def mcmc_step(self, i, force_mask=None):
+        """``sampler.py:104-155``.  ``force_mask`` (parity-harness hook, not in the
+        reference) overrides the accept decisions so that two implementations can
+        be compared in lock-step after a tie."""
         S = self.num_samplers
         centers = self.flip_positions[i]                             # :106
         combined = np.prod(self._flipper_padded[centers], 1)         # :114-115
@@ -92,6 +94,9 @@ class Sampler(object):
         log_ratio = (flipped_factors - self.current_factors).sum(1)  # :124 inner
         accept_prob = np.abs(np.exp(log_ratio)) ** 2                 # :123-124
         mask = accept_prob > self.accept_sample[i]                   # :125 strict
+        self.last_own_mask = mask
+        if force_mask is not None:
+            mask = np.asarray(force_mask, bool)
         self.current_samples[mask] = flipped[mask]                   # :128-130
         self.current_factors[mask] = flipped_factors[mask]           # :131-133
         self.last_log_ratio, self.last_mask = log_ratio, mask

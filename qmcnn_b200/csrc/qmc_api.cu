@@ -181,7 +181,8 @@ int qmc_logpsi_forward(qmc_handle* h, const int8_t* spins, int N, float* cache, 
 int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* workspace, int S,
                          int num_flips, int64_t step0, int64_t n_steps, const int32_t* flip_pos,
                          const float* uniforms, uint64_t seed, int64_t chain_id0, int64_t therm_its,
-                         int64_t its_per_sample, int8_t* samples, uint8_t* accept_trace,
+                         int64_t its_per_sample, int8_t* samples, int64_t n_sample_slots,
+                         uint8_t* accept_trace,
                          float* logratio_trace, unsigned long long* n_accept, void* stream) {
     QMC_ENTER(h);
     int rc = QMC_OK;
@@ -191,12 +192,12 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
         rc = fail(h, QMC_ERR_UNSUPPORTED, "sweep: num_flips must be 1 or 2");
     else if ((flip_pos == nullptr) != (uniforms == nullptr))
         rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep: flip_pos and uniforms must both be given or both be NULL");
-    else if (samples && its_per_sample < 1)
-        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep: its_per_sample must be positive");
+    else if (samples && (its_per_sample < 1 || n_sample_slots < 1))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep: its_per_sample and n_sample_slots must be positive");
     else if (S > 0 && n_steps > 0) {
         SweepArgs a{spins, cache, workspace, S, num_flips, step0, n_steps, flip_pos, uniforms,
                     seed, chain_id0, therm_its, its_per_sample > 0 ? its_per_sample : 1, samples,
-                    accept_trace, logratio_trace, n_accept};
+                    n_sample_slots, accept_trace, logratio_trace, n_accept};
         cudaError_t e = launch_sweep(h, a, (cudaStream_t)stream, h->err);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep");
     }

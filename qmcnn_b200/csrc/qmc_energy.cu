@@ -8,12 +8,22 @@
 // K1) and accumulates exp(log_pop) in registers.
 #include "qmc_host.h"
 
+// Compiled twice like qmc_sweep.cu: QMC_MAXW=8 (255 registers) and 16 (128 registers).
+#ifndef QMC_MAXW
+#define QMC_MAXW 8
+#endif
+#define QMC_CAT2(a, b) a##b
+#define QMC_CAT(a, b) QMC_CAT2(a, b)
+#define K_ENERGY QMC_CAT(k_energy_w, QMC_MAXW)
+
 namespace qmc {
+
+constexpr bool kBig = QMC_MAXW <= 8;
 
 constexpr int kEnergyChunks = 8;   // site chunks per sample (warp tasks = N * chunks)
 
-__global__ void __launch_bounds__(512)
-k_energy(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
+__global__ void __launch_bounds__(QMC_MAXW * 32, 1)
+K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
          const float* __restrict__ cache_all, int hamiltonian, float2* __restrict__ partial,
          int nchunks, EvalPlan pl, bool allow_tiled) {
     extern __shared__ float4 smem4[];
@@ -47,7 +57,7 @@ k_energy(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
             float dre, dim, sn, cn;
             if (hamiltonian == QMC_HAMILTONIAN_TFIM) {
                 const FlipBox box = make_box(m, 1, i, -1);
-                warp_eval_flip<true>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride, box,
+                warp_eval_flip<true, kBig>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride, box,
                                      lane, allow_tiled, reg, dre, dim);
                 const float amp = expf(dre);
                 sincosf(dim, &sn, &cn);
@@ -61,7 +71,7 @@ k_energy(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
                     if (j == i) { are += 1.f; continue; }          // L == 1 along d: s_i s_i = 1
                     if (spins_s[i] == spins_s[j]) { are += 1.f; continue; }  // -(1-1) exp + 1
                     const FlipBox box = make_box(m, 2, i, j);
-                    warp_eval_flip<true>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride,
+                    warp_eval_flip<true, kBig>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride,
                                          box, lane, allow_tiled, reg, dre, dim);
                     const float amp = expf(dre);
                     sincosf(dim, &sn, &cn);
@@ -73,6 +83,22 @@ k_energy(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
         if (lane == 0) partial[(size_t)s * nchunks + chunk] = make_float2(are, aim);
     }
 }
+
+cudaError_t QMC_CAT(launch_energy_main_w, QMC_MAXW)(const qmc_handle* h, const int8_t* spins, int N,
+                                                    const float* cache, int hamiltonian, float2* partial,
+                                                    int nchunks, const EvalPlan& pl, const WarpGrid& g,
+                                                    cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(K_ENERGY, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    K_ENERGY<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, spins, N, cache, hamiltonian, partial,
+                                                    nchunks, pl, h->allow_tiled);
+    return cudaGetLastError();
+}
+
+#if QMC_MAXW == 8
+cudaError_t launch_energy_main_w16(const qmc_handle* h, const int8_t* spins, int N, const float* cache,
+                                   int hamiltonian, float2* partial, int nchunks, const EvalPlan& pl,
+                                   const WarpGrid& g, cudaStream_t st);
 
 // one thread per sample: ordered chunk sum, diagonal term, per-spin normalisation
 __global__ void k_energy_finish(DevModel m, const int8_t* __restrict__ spins, int N, int hamiltonian,
@@ -136,15 +162,14 @@ cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, c
     EvalPlan pl = eval_plan(m, h0, h0, true);
     WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, (long long)N * nchunks);
     if (!g.ok) { err = "local_energy: model does not fit in shared memory"; return cudaErrorInvalidValue; }
-    e = cudaFuncSetAttribute(k_energy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    if (e != cudaSuccess) return e;
-    k_energy<<<g.grid, g.warps * 32, g.smem, st>>>(m, h->d_params, spins, N, cache, hamiltonian, partial,
-                                                  nchunks, pl, h->allow_tiled);
-    e = cudaGetLastError();
+    e = g.warps <= 8 ? launch_energy_main_w8(h, spins, N, cache, hamiltonian, partial, nchunks, pl, g, st)
+                     : launch_energy_main_w16(h, spins, N, cache, hamiltonian, partial, nchunks, pl, g, st);
     if (e != cudaSuccess) return e;
     k_energy_finish<<<(N + 127) / 128, 128, 0, st>>>(m, spins, N, hamiltonian, field_h, partial, nchunks,
                                                     reinterpret_cast<float2*>(e_loc), moments);
     return cudaGetLastError();
 }
+
+#endif // QMC_MAXW == 8
 
 } // namespace qmc

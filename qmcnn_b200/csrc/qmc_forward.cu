@@ -14,7 +14,7 @@ namespace qmc {
 
 constexpr int kFwdBlock = 8;   // output block side per warp task
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256, 1)
 k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
           float* __restrict__ cache_all, float2* __restrict__ factors, float2* __restrict__ logpsi,
           int buf_in_floats, int buf_out_floats, bool allow_tiled) {
@@ -60,7 +60,7 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
                 __syncwarp();
                 if (!last) {
                     float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
-                    conv_region(L, m.k, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
+                    conv_region<true>(L, m.k, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
                                 [&](int, int y, int x, int cog, float4 a) {
                                     a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
                                     plane4[cog * n + (ry + y) * Lx + rx + x] = a;
@@ -68,7 +68,7 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
                 } else {
                     float4* tout4 = reinterpret_cast<float4*>(tout);
                     const int rarea = rh * rw;
-                    conv_region(L, m.k, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
+                    conv_region<true>(L, m.k, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
                                 [&](int pos, int, int, int cog, float4 a) { tout4[cog * rarea + pos] = a; });
                     __syncwarp();
                     for (int pos = lane; pos < rarea; pos += kWarp) {

@@ -101,7 +101,7 @@ struct SweepArgs {
     const int32_t* flip_pos; const float* uniforms;
     unsigned long long seed; long long chain_id0;
     long long therm_its, its_per_sample;
-    int8_t* samples; uint8_t* accept_trace; float* logratio_trace;
+    int8_t* samples; long long n_sample_slots; uint8_t* accept_trace; float* logratio_trace;
     unsigned long long* n_accept;
 };
 

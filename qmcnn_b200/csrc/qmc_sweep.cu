@@ -12,10 +12,21 @@
 // executed inside the step loop.
 #include "qmc_host.h"
 
+// Compiled twice (Makefile): QMC_MAXW=8 (<= 8 warps per CTA, 255 registers, big register
+// tiles - the large-model variant) and QMC_MAXW=16 (128 registers, small models).
+#ifndef QMC_MAXW
+#define QMC_MAXW 8
+#endif
+
 namespace qmc {
 
-__global__ void __launch_bounds__(512)
-k_sweep(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, bool allow_tiled) {
+#define QMC_CAT2(a, b) a##b
+#define QMC_CAT(a, b) QMC_CAT2(a, b)
+#define K_SWEEP QMC_CAT(k_sweep_w, QMC_MAXW)
+constexpr bool kBig = QMC_MAXW <= 8;
+
+__global__ void __launch_bounds__(QMC_MAXW * 32, 1)
+K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, bool allow_tiled) {
     extern __shared__ float4 smem4[];
     float* sp = reinterpret_cast<float*>(smem4);
     load_params_to_smem(m, params, sp);
@@ -64,7 +75,7 @@ k_sweep(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
                 const FlipBox box = make_box(m, a.num_flips, f0, f1);
                 Region reg;
                 float dim;
-                warp_eval_flip<false>(m, sp, buf0, buf1, spins_s, cache, staging, newf, pl.nfstride,
+                warp_eval_flip<false, kBig>(m, sp, buf0, buf1, spins_s, cache, staging, newf, pl.nfstride,
                                       box, lane, allow_tiled, reg, dre, dim);
                 const float amp = expf(dre);            // |exp(z)| = exp(Re z)
                 accept = amp * amp > u;                 // strict, sampler.py:125
@@ -78,18 +89,31 @@ k_sweep(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
                         const LayerInfo& L = m.layer[l];
                         const int rarea = rh * rw, ncg = L.coutp >> 2;
                         float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
-                        for (int idx = lane; idx < ncg * rarea; idx += kWarp) {
-                            const int cg = idx / rarea, pos = idx - cg * rarea;
-                            const int y = pos / rw, x = pos - y * rw;
-                            const int site = wrapi(ry + y, Ly) * Lx + wrapi(rx + x, Lx);
-                            plane4[cg * n + site] = ldcg4(staging + stg + (size_t)idx * 4);
+                        const FastDiv drw(rw), darea(rarea);
+                        for (int base = 0; base < ncg * rarea; base += 4 * kWarp) {
+                            float4 v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int idx = base + j * kWarp + lane;
+                                if (idx < ncg * rarea) v[j] = ldcg4(staging + stg + (size_t)idx * 4);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int idx = base + j * kWarp + lane;
+                                if (idx >= ncg * rarea) continue;
+                                const int cg = darea.div(idx), pos = idx - cg * rarea;
+                                const int y = drw.div(pos), x = pos - y * rw;
+                                const int site = wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx);
+                                plane4[cg * n + site] = v[j];
+                            }
                         }
                         stg += L.coutp * rarea;
                         ry -= p; rx -= p; rh += 2 * p; rw += 2 * p;
                     }
+                    const FastDiv dregw(reg.rw);
                     for (int pos = lane; pos < reg.rh * reg.rw; pos += kWarp) {
-                        const int y = pos / reg.rw, x = pos - y * reg.rw;
-                        const int site = wrapi(reg.ry + y, Ly) * Lx + wrapi(reg.rx + x, Lx);
+                        const int y = dregw.div(pos), x = pos - y * reg.rw;
+                        const int site = wrap1(reg.ry + y, Ly) * Lx + wrap1(reg.rx + x, Lx);
                         cache[m.fre_off + site] = newf[pos];
                     }
                     if (lane == 0) {
@@ -107,8 +131,10 @@ k_sweep(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
             // sample write-out AFTER the update (sampler.py:135-152)
             if (a.samples && step >= a.therm_its && (step - a.therm_its) % a.its_per_sample == 0) {
                 const long long j = (step - a.therm_its) / a.its_per_sample;
+                if (j < a.n_sample_slots) {
                 int8_t* dst = a.samples + ((size_t)j * a.S + chain) * n;
                 for (int i = lane; i < n; i += kWarp) dst[i] = spins_s[i];
+                }
             }
         }
         for (int i = lane; i < n; i += kWarp) gspins[i] = spins_s[i];
@@ -116,6 +142,18 @@ k_sweep(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
     }
     if (a.n_accept && lane == 0 && accepted) atomicAdd(a.n_accept, accepted);
 }
+
+cudaError_t QMC_CAT(launch_sweep_w, QMC_MAXW)(const qmc_handle* h, const SweepArgs& a, const EvalPlan& pl,
+                                              const WarpGrid& g, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(K_SWEEP, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    K_SWEEP<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, a, pl, h->allow_tiled);
+    return cudaGetLastError();
+}
+
+#if QMC_MAXW == 8
+cudaError_t launch_sweep_w16(const qmc_handle* h, const SweepArgs& a, const EvalPlan& pl,
+                             const WarpGrid& g, cudaStream_t st);
 
 int sweep_slots(const qmc_handle* h, int S, int num_flips, EvalPlan* plan, WarpGrid* grid) {
     const DevModel& m = h->m;
@@ -135,10 +173,8 @@ cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t s
     const int slots = sweep_slots(h, a.S, a.num_flips, &pl, &g);
     if (slots == -1) { err = "sweep: flip box does not fit the lattice (need h0 + r - 1 <= L for deep models)"; return cudaErrorInvalidValue; }
     if (slots < 0) { err = "sweep: model does not fit in shared memory"; return cudaErrorInvalidValue; }
-    cudaError_t e = cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    if (e != cudaSuccess) return e;
-    k_sweep<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, a, pl, h->allow_tiled);
-    return cudaGetLastError();
+    return g.warps <= 8 ? launch_sweep_w8(h, a, pl, g, st) : launch_sweep_w16(h, a, pl, g, st);
 }
+#endif
 
 } // namespace qmc

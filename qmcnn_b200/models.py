@@ -66,7 +66,7 @@ class _Model(object):
     def forward_unpadded(self, spins, system_shape, want_factors=True, want_logpsi=False, cache=None):
         """K1 on UN-padded int8 spins (N, Ly*Lx). Returns (factors, logpsi, cache)."""
         h = self.handle(system_shape)
-        spins = spins.reshape(-1, h.n)
+        spins = torch.as_tensor(spins, device=self.device).reshape(-1, h.n)
         if spins.dtype != torch.int8:
             spins = spins.to(torch.int8)
         spins = spins.contiguous()

@@ -147,7 +147,7 @@ class Sampler(object):
             fp.data_ptr() if fed else None, ua.data_ptr() if fed else None,
             self.seed, self.chain_id0,
             self.therm_its + (0 if fed else self._step_base), self.its_per_sample,
-            self._samples.data_ptr(),
+            self._samples.data_ptr(), self.samples_per_sampler,
             self.accept_trace.data_ptr() if trace else None,
             self.logratio_trace.data_ptr() if trace else None,
             self._n_accept.data_ptr(), _stream_ptr(self.device)), "qmc_metropolis_sweep")
