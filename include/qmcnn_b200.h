@@ -134,6 +134,8 @@ int qmc_logpsi_backward(qmc_handle* h, const int8_t* spins, const float* weights
  * and MUFU ex2 (Gop/s) issue peaks of `device` - the roofline denominators
  * MEASURED_PEAKS.json does not carry. */
 int qmc_diag_peaks(int device, double* fp32_tflops /*host*/, double* mufu_gops /*host*/);
+/* same, plus the packed fma.rn.f32x2 (FFMA2) rate in TFLOP/s */
+int qmc_diag_peaks2(int device, double* fp32_tflops, double* ffma2_tflops, double* mufu_gops);
 
 /* library build info, host string */
 const char* qmc_version(void);

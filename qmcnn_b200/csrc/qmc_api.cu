@@ -52,6 +52,7 @@ static bool build_model(const qmc_model_desc* d, DevModel& m, std::string& err) 
     if (m.bias_vis_off >= 0) { m.sp_vis_off = soff; soff += 4; }
     m.P = off;
     m.smem_param_floats = round4(soff);
+    m.use_const = m.smem_param_floats <= kConstFloats ? 1 : 0;
     m.fre_off = coff; coff += round4(m.n);
     m.fim_off = coff; coff += round4(m.n);
     m.cache_floats = coff;
@@ -86,10 +87,22 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     h->allow_tiled = !(fg && fg[0] == '1');
     e = cudaMalloc(&h->d_params, sizeof(float) * (size_t)m.P);
     if (e == cudaSuccess) e = cudaMemset(h->d_params, 0, sizeof(float) * (size_t)m.P);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_params_padded, sizeof(float) * (size_t)m.smem_param_floats);
+    if (e == cudaSuccess) e = cudaMemset(h->d_params_padded, 0, sizeof(float) * (size_t)m.smem_param_floats);
+    const char* fp = std::getenv("QMC_FORCE_PERSISTENT");
+    h->allow_batched = !(fp && fp[0] == '1');
+    const char* sp = std::getenv("QMC_SWEEP_PATH");
+    h->batched_sweep = h->allow_batched && sp && std::strcmp(sp, "batched") == 0;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(params)"); }
     if ((size_t)m.smem_param_floats * 4 > h->max_smem) {
-        cudaFree(h->d_params); delete h;
+        cudaFree(h->d_params); cudaFree(h->d_params_padded); delete h;
         return fail(nullptr, QMC_ERR_UNSUPPORTED, "parameters do not fit in shared memory");
     }
     *out = h;
@@ -102,6 +115,13 @@ int qmc_destroy(qmc_handle* h) {
     cudaGetDevice(&prev);
     cudaSetDevice(h->device);
     cudaFree(h->d_params);
+    cudaFree(h->d_params_padded);
+    for (int i = 0; i < 2; ++i) {
+        if (h->side_stream[i]) cudaStreamDestroy(h->side_stream[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_mid) cudaEventDestroy(h->ev_mid);
     cudaSetDevice(prev);
     delete h;
     return QMC_OK;
@@ -117,13 +137,22 @@ size_t qmc_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips) {
     EvalPlan pl;
     const int slots = sweep_slots(h, S, num_flips, &pl, nullptr);
     if (slots < 0) return 0;
-    const size_t f = (size_t)slots * pl.staging_floats;
+    size_t f = (size_t)slots * pl.staging_floats;
+    if (num_flips == 1 && h->batched_sweep && batched_supported(h)) {
+        const int half = (S + 1) / 2;     // the chains may be split over two streams, each with its own scratch
+        const size_t b = 2 * (batched_staging_floats(h, half) + batched_scratch_floats(half)) + 16;
+        if (b > f) f = b;
+    }
     return f ? f : 4;
 }
 
 size_t qmc_energy_workspace_floats(const qmc_handle* h, int N) {
     if (!h || N < 1) return 0;
-    return (size_t)N * h->m.cache_floats + (size_t)N * energy_chunks(h) * 2;
+    size_t f = (size_t)N * h->m.cache_floats + (size_t)N * energy_chunks(h) * 2;
+    if (h->allow_batched && batched_supported(h))   // + per-site terms and one chunk of staged windows
+        f += (size_t)N * h->m.n * 2 + batched_staging_floats(h, kEnergyChunkItems) +
+             batched_scratch_floats(kEnergyChunkItems);
+    return f;
 }
 
 size_t qmc_backward_workspace_floats(const qmc_handle* h, int N) {
@@ -146,6 +175,7 @@ int qmc_set_params(qmc_handle* h, const float* params, void* stream) {
     else {
         cudaError_t e = cudaMemcpyAsync(h->d_params, params, sizeof(float) * (size_t)h->m.P,
                                         cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = repack_params(h, (cudaStream_t)stream);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "set_params");
     }
     QMC_LEAVE(h);
@@ -198,7 +228,9 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
         SweepArgs a{spins, cache, workspace, S, num_flips, step0, n_steps, flip_pos, uniforms,
                     seed, chain_id0, therm_its, its_per_sample > 0 ? its_per_sample : 1, samples,
                     n_sample_slots, accept_trace, logratio_trace, n_accept};
-        cudaError_t e = launch_sweep(h, a, (cudaStream_t)stream, h->err);
+        cudaError_t e = (num_flips == 1 && h->batched_sweep && batched_supported(h))
+                            ? launch_sweep_batched(h, a, (cudaStream_t)stream, h->err)
+                            : launch_sweep(h, a, (cudaStream_t)stream, h->err);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep");
     }
     QMC_LEAVE(h);

@@ -15,6 +15,31 @@
 
 namespace qmc {
 
+// flat caller-order parameters -> padded block layout (the image c_params / shared memory hold)
+__global__ void k_repack_params(DevModel m, const float* __restrict__ params, float* __restrict__ padded) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m.smem_param_floats) return;
+    float v = 0.f;
+    for (int l = 0; l < m.D; ++l) {
+        const LayerInfo& L = m.layer[l];
+        const int rows = m.k * m.k * L.cin;
+        if (i >= L.sw_off && i < L.sw_off + rows * L.coutp) {
+            const int row = (i - L.sw_off) / L.coutp, co = (i - L.sw_off) - row * L.coutp;
+            if (co < L.cout) v = params[L.w_off + row * L.cout + co];
+        } else if (i >= L.sb_off && i < L.sb_off + L.cout) {
+            v = params[L.b_off + i - L.sb_off];
+        }
+    }
+    if (m.bias_vis_off >= 0 && i >= m.sp_vis_off && i < m.sp_vis_off + 2) v = params[m.bias_vis_off + i - m.sp_vis_off];
+    padded[i] = v;
+}
+
+cudaError_t repack_params(const qmc_handle* h, cudaStream_t st) {
+    const int nthr = 256, nblk = (h->m.smem_param_floats + nthr - 1) / nthr;
+    k_repack_params<<<nblk, nthr, 0, st>>>(h->m, h->d_params, h->d_params_padded);
+    return cudaGetLastError();
+}
+
 constexpr int kBwdThreads = 256;
 
 __device__ __forceinline__ float2 ctanh_stable(float a, float b) {

@@ -24,6 +24,24 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a
 }
 
 template <int ILP>
+__global__ void __launch_bounds__(256) k_fma2_peak(float* out, int iters, float a, float b) {
+    float2 x[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) x[i] = __ffma2_rn(x[i], a2, b2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i].x + x[i].y;
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <int ILP>
 __global__ void __launch_bounds__(256) k_mufu_peak(float* out, int iters) {
     float x[ILP];
 #pragma unroll
@@ -42,7 +60,7 @@ __global__ void __launch_bounds__(256) k_mufu_peak(float* out, int iters) {
 
 } // namespace
 
-extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops) {
+static int diag_peaks_impl(int device, double* fp32_tflops, double* mufu_gops, double* ffma2_tflops) {
     int prev = 0;
     cudaGetDevice(&prev);
     if (cudaSetDevice(device) != cudaSuccess) return QMC_ERR_NO_DEVICE;
@@ -55,7 +73,7 @@ extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops
     cudaEventCreate(&e1);
     constexpr int ILP = 8;
     const int grid = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
-    double best_f = 0, best_m = 0;
+    double best_f = 0, best_m = 0, best_f2 = 0;
     for (int rep = 0; rep < 4; ++rep) {
         float ms = 0;
         cudaEventRecord(e0);
@@ -65,6 +83,12 @@ extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops
         cudaEventElapsedTime(&ms, e0, e1);
         const double flop = 2.0 * grid * threads * (double)iters * 8 * ILP;
         if (ms > 0 && flop / (ms * 1e-3) * 1e-12 > best_f) best_f = flop / (ms * 1e-3) * 1e-12;
+        cudaEventRecord(e0);
+        k_fma2_peak<ILP><<<grid, threads>>>(d, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms > 0 && 2.0 * flop / (ms * 1e-3) * 1e-12 > best_f2) best_f2 = 2.0 * flop / (ms * 1e-3) * 1e-12;
         cudaEventRecord(e0);
         k_mufu_peak<ILP><<<grid, threads>>>(d, iters / 4);
         cudaEventRecord(e1);
@@ -80,5 +104,14 @@ extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops
     cudaSetDevice(prev);
     if (fp32_tflops) *fp32_tflops = best_f;
     if (mufu_gops) *mufu_gops = best_m;
+    if (ffma2_tflops) *ffma2_tflops = best_f2;
     return e == cudaSuccess ? QMC_OK : QMC_ERR_CUDA;
+}
+
+extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops) {
+    return diag_peaks_impl(device, fp32_tflops, mufu_gops, nullptr);
+}
+
+extern "C" int qmc_diag_peaks2(int device, double* fp32_tflops, double* ffma2_tflops, double* mufu_gops) {
+    return diag_peaks_impl(device, fp32_tflops, mufu_gops, ffma2_tflops);
 }

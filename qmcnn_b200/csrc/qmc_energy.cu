@@ -25,12 +25,16 @@ constexpr int kEnergyChunks = 8;   // site chunks per sample (warp tasks = N * c
 __global__ void __launch_bounds__(QMC_MAXW * 32, 1)
 K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
          const float* __restrict__ cache_all, int hamiltonian, float2* __restrict__ partial,
-         int nchunks, EvalPlan pl, bool allow_tiled) {
+         int nchunks, EvalPlan pl, int allow_tiled) {
     extern __shared__ float4 smem4[];
-    float* sp = reinterpret_cast<float*>(smem4);
-    load_params_to_smem(m, params, sp);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    char* wmem = reinterpret_cast<char*>(sp + m.smem_param_floats) + (size_t)warp * pl.per_warp_bytes;
+    float* smem_f = reinterpret_cast<float*>(smem4);
+    load_params_to_smem(m, params, smem_f);
+    const float* sp = smem_f;
+    // broadcast from lane 0 so the compiler knows the warp index (and everything derived from it:
+    // chain, task, loop bounds) is warp-uniform and may use the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    char* wmem = reinterpret_cast<char*>(smem_f + m.smem_param_floats) + (size_t)warp * pl.per_warp_bytes;
     float* buf0 = reinterpret_cast<float*>(wmem);
     float* buf1 = buf0 + pl.buf_floats[0];
     float* newf = buf1 + pl.buf_floats[1];
@@ -69,7 +73,8 @@ K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
                     const int j = d == 0 ? (y + 1 == Ly ? 0 : y + 1) * Lx + x
                                          : y * Lx + (x + 1 == Lx ? 0 : x + 1);
                     if (j == i) { are += 1.f; continue; }          // L == 1 along d: s_i s_i = 1
-                    if (spins_s[i] == spins_s[j]) { are += 1.f; continue; }  // -(1-1) exp + 1
+                    const bool aligned = __shfl_sync(0xffffffffu, (int)(spins_s[i] == spins_s[j]), 0) != 0;
+                    if (aligned) { are += 1.f; continue; }                   // -(1-1) exp + 1
                     const FlipBox box = make_box(m, 2, i, j);
                     warp_eval_flip<true, kBig>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride,
                                          box, lane, allow_tiled, reg, dre, dim);
@@ -91,7 +96,7 @@ cudaError_t QMC_CAT(launch_energy_main_w, QMC_MAXW)(const qmc_handle* h, const i
     cudaError_t e = cudaFuncSetAttribute(K_ENERGY, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     K_ENERGY<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, spins, N, cache, hamiltonian, partial,
-                                                    nchunks, pl, h->allow_tiled);
+                                                    nchunks, pl, h->allow_tiled ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -142,6 +147,14 @@ __global__ void k_energy_finish(DevModel m, const int8_t* __restrict__ spins, in
     }
 }
 
+cudaError_t launch_energy_finish(const qmc_handle* h, const int8_t* spins, int N, int hamiltonian, float field_h,
+                                 const float2* partial, int nchunks, float* e_loc, double* moments,
+                                 cudaStream_t st) {
+    k_energy_finish<<<(N + 127) / 128, 128, 0, st>>>(h->m, spins, N, hamiltonian, field_h, partial, nchunks,
+                                                    reinterpret_cast<float2*>(e_loc), moments);
+    return cudaGetLastError();
+}
+
 int energy_chunks(const qmc_handle* h) { return h->m.n < kEnergyChunks ? h->m.n : kEnergyChunks; }
 
 cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins,
@@ -159,15 +172,21 @@ cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, c
     float2* partial = reinterpret_cast<float2*>(workspace + (size_t)N * m.cache_floats);
     cudaError_t e = launch_forward(h, spins, N, cache, nullptr, nullptr, st, err);
     if (e != cudaSuccess) return e;
+    if (!heis && h->allow_batched && batched_supported(h)) {
+        // layer-synchronous batched evaluation of all N * n single-flip configurations
+        float2* terms = partial + (size_t)N * nchunks;
+        float* scratch = reinterpret_cast<float*>(terms + (size_t)N * m.n);
+        e = launch_energy_batched(h, spins, N, cache, scratch, kEnergyChunkItems, terms, st, err);
+        if (e != cudaSuccess) return e;
+        return launch_energy_finish(h, spins, N, hamiltonian, field_h, terms, m.n, e_loc, moments, st);
+    }
     EvalPlan pl = eval_plan(m, h0, h0, true);
     WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, (long long)N * nchunks);
     if (!g.ok) { err = "local_energy: model does not fit in shared memory"; return cudaErrorInvalidValue; }
     e = g.warps <= 8 ? launch_energy_main_w8(h, spins, N, cache, hamiltonian, partial, nchunks, pl, g, st)
                      : launch_energy_main_w16(h, spins, N, cache, hamiltonian, partial, nchunks, pl, g, st);
     if (e != cudaSuccess) return e;
-    k_energy_finish<<<(N + 127) / 128, 128, 0, st>>>(m, spins, N, hamiltonian, field_h, partial, nchunks,
-                                                    reinterpret_cast<float2*>(e_loc), moments);
-    return cudaGetLastError();
+    return launch_energy_finish(h, spins, N, hamiltonian, field_h, partial, nchunks, e_loc, moments, st);
 }
 
 #endif // QMC_MAXW == 8

@@ -17,16 +17,20 @@ constexpr int kFwdBlock = 8;   // output block side per warp task
 __global__ void __launch_bounds__(256, 1)
 k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
           float* __restrict__ cache_all, float2* __restrict__ factors, float2* __restrict__ logpsi,
-          int buf_in_floats, int buf_out_floats, bool allow_tiled) {
+          int buf_in_floats, int buf_out_floats, int allow_tiled) {
     extern __shared__ float4 smem4[];
-    float* sp = reinterpret_cast<float*>(smem4);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    float* wbase = sp + m.smem_param_floats + warp * (buf_in_floats + buf_out_floats);
+    float* smem_f = reinterpret_cast<float*>(smem4);
+    // broadcast from lane 0 so the compiler knows the warp index (and everything derived from it:
+    // chain, task, loop bounds) is warp-uniform and may use the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* wbase = smem_f + m.smem_param_floats + warp * (buf_in_floats + buf_out_floats);
     float* tin = wbase;
     float* tout = wbase + buf_in_floats;
-    float* red = sp + m.smem_param_floats + nwarps * (buf_in_floats + buf_out_floats); // 2*blockDim floats
+    float* red = smem_f + m.smem_param_floats + nwarps * (buf_in_floats + buf_out_floats); // 2*blockDim floats
     int8_t* spins_s = reinterpret_cast<int8_t*>(red + 2 * blockDim.x);
-    load_params_to_smem(m, params, sp);
+    load_params_to_smem(m, params, smem_f);
+    const float* sp = smem_f;
 
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n;
     const int nby = (Ly + kFwdBlock - 1) / kFwdBlock, nbx = (Lx + kFwdBlock - 1) / kFwdBlock;
@@ -60,7 +64,7 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
                 __syncwarp();
                 if (!last) {
                     float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
-                    conv_region<true>(L, m.k, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
+                    conv_region<true>(m, l, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
                                 [&](int, int y, int x, int cog, float4 a) {
                                     a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
                                     plane4[cog * n + (ry + y) * Lx + rx + x] = a;
@@ -68,7 +72,7 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
                 } else {
                     float4* tout4 = reinterpret_cast<float4*>(tout);
                     const int rarea = rh * rw;
-                    conv_region<true>(L, m.k, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
+                    conv_region<true>(m, l, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
                                 [&](int pos, int, int, int cog, float4 a) { tout4[cog * rarea + pos] = a; });
                     __syncwarp();
                     for (int pos = lane; pos < rarea; pos += kWarp) {
@@ -134,7 +138,7 @@ cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, floa
     int grid = N < h->num_sms * 4 ? N : h->num_sms * 4;
     k_forward<<<grid, warps * 32, smem, st>>>(m, h->d_params, spins, N, cache,
                                              reinterpret_cast<float2*>(factors),
-                                             reinterpret_cast<float2*>(logpsi), bin, bout, h->allow_tiled);
+                                             reinterpret_cast<float2*>(logpsi), bin, bout, h->allow_tiled ? 1 : 0);
     return cudaGetLastError();
 }
 

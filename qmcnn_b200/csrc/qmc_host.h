@@ -9,16 +9,22 @@ struct qmc_handle {
     int device = 0;
     qmc_model_desc desc{};
     qmc::DevModel m{};
-    float* d_params = nullptr;
+    float* d_params = nullptr;         // caller's flat order
+    float* d_params_padded = nullptr;  // padded block layout (shared / constant memory image)
     std::string err;
     int num_sms = 0;
     size_t max_smem = 0;   // opt-in dynamic shared memory per CTA
     bool allow_tiled = true;  // QMC_FORCE_GENERIC=1 disables the specialised conv instances
+    bool allow_batched = true;  // QMC_FORCE_PERSISTENT=1 disables the layer-synchronous batched path (energy + sweep)
+    bool batched_sweep = false; // QMC_SWEEP_PATH=batched: use the batched path for the sweep too (default: persistent
+                                // kernel, which is faster at a few thousand chains per GPU - DESIGN.md)
+    cudaStream_t side_stream[2] = {nullptr, nullptr};   // batched sweep: capturable streams, event-ordered with the caller's
+    cudaEvent_t ev_in = nullptr, ev_mid = nullptr, ev_out[2] = {nullptr, nullptr};
 };
 
 namespace qmc {
 
-inline int round4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 
 // shared-memory plan of warp_eval_flip for boxes up to h0max x w0max
 struct EvalPlan {
@@ -106,6 +112,7 @@ struct SweepArgs {
 };
 
 // launchers (each in its own .cu); return cudaError_t of the launch
+cudaError_t repack_params(const qmc_handle* h, cudaStream_t st);
 cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
                            float* factors, float* logpsi, cudaStream_t st, std::string& err);
 cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
@@ -116,6 +123,18 @@ cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const floa
                             float* workspace, float* grad, cudaStream_t st, std::string& err);
 
 int sweep_slots(const qmc_handle* h, int S, int num_flips, EvalPlan* plan, WarpGrid* grid);
+// layer-synchronous batched path (qmc_batched.cu)
+bool batched_supported(const qmc_handle* h);
+size_t batched_staging_floats(const qmc_handle* h, int n_items);
+size_t batched_scratch_floats(int n_items);
+cudaError_t launch_sweep_batched(const qmc_handle* h, const SweepArgs& s, cudaStream_t caller, std::string& err);
+cudaError_t launch_energy_batched(const qmc_handle* h, const int8_t* spins, int N, const float* cache,
+                                  float* scratch, int chunk_items, float2* terms, cudaStream_t st,
+                                  std::string& err);
+constexpr int kEnergyChunkItems = 32768;   // (sample, site) items evaluated per batched pass
+cudaError_t launch_energy_finish(const qmc_handle* h, const int8_t* spins, int N, int hamiltonian, float field_h,
+                                 const float2* partial, int nchunks, float* e_loc, double* moments,
+                                 cudaStream_t st);
 int energy_chunks(const qmc_handle* h);
 size_t backward_workspace_floats(const qmc_handle* h, int N);
 

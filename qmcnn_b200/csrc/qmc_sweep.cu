@@ -26,12 +26,16 @@ namespace qmc {
 constexpr bool kBig = QMC_MAXW <= 8;
 
 __global__ void __launch_bounds__(QMC_MAXW * 32, 1)
-K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, bool allow_tiled) {
+K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, int allow_tiled) {
     extern __shared__ float4 smem4[];
-    float* sp = reinterpret_cast<float*>(smem4);
-    load_params_to_smem(m, params, sp);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    char* wmem = reinterpret_cast<char*>(sp + m.smem_param_floats) + (size_t)warp * pl.per_warp_bytes;
+    float* smem_f = reinterpret_cast<float*>(smem4);
+    load_params_to_smem(m, params, smem_f);
+    const float* sp = smem_f;
+    // broadcast from lane 0 so the compiler knows the warp index (and everything derived from it:
+    // chain, task, loop bounds) is warp-uniform and may use the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    char* wmem = reinterpret_cast<char*>(smem_f + m.smem_param_floats) + (size_t)warp * pl.per_warp_bytes;
     float* buf0 = reinterpret_cast<float*>(wmem);
     float* buf1 = buf0 + pl.buf_floats[0];
     float* newf = buf1 + pl.buf_floats[1];
@@ -66,6 +70,10 @@ K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
                 if (a.num_flips > 1) f1 = (int)__umulhi(r.y, (uint32_t)n);
                 u = (float)(r.w >> 8) * 5.9604644775390625e-8f;   // 2^-24
             }
+            // loaded values are warp-uniform by construction; tell the compiler (uniform datapath)
+            f0 = __shfl_sync(0xffffffffu, f0, 0);
+            f1 = __shfl_sync(0xffffffffu, f1, 0);
+            u = __shfl_sync(0xffffffffu, u, 0);
             bool accept;
             float dre = 0.f;
             if (a.num_flips > 1 && f0 == f1) {
@@ -78,7 +86,7 @@ K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
                 warp_eval_flip<false, kBig>(m, sp, buf0, buf1, spins_s, cache, staging, newf, pl.nfstride,
                                       box, lane, allow_tiled, reg, dre, dim);
                 const float amp = expf(dre);            // |exp(z)| = exp(Re z)
-                accept = amp * amp > u;                 // strict, sampler.py:125
+                accept = __shfl_sync(0xffffffffu, (int)(amp * amp > u), 0) != 0;   // strict, sampler.py:125
                 if (accept) {
                     // commit: new hidden activations (from staging), new factors, spins
                     int rh = box.h0 + 2 * p, rw = box.w0 + 2 * p;
@@ -147,7 +155,7 @@ cudaError_t QMC_CAT(launch_sweep_w, QMC_MAXW)(const qmc_handle* h, const SweepAr
                                               const WarpGrid& g, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(K_SWEEP, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
-    K_SWEEP<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, a, pl, h->allow_tiled);
+    K_SWEEP<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, a, pl, h->allow_tiled ? 1 : 0);
     return cudaGetLastError();
 }
 

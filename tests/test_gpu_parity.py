@@ -252,6 +252,49 @@ def test_incremental_cache_equals_full_forward_after_many_flips():
     assert a.acceptance_count > 0
 
 
+@pytest.mark.parametrize("layers,shape,S", [([16, 16, 16, 8], (12, 13), 70), ([8, 8, 8], (10, 10), 33),
+                                            ([16, 16, 16, 16, 16, 8], (20, 20), 21)])
+def test_batched_path_is_bit_identical_to_persistent(layers, shape, S):
+    """The layer-synchronous batched kernels (uniform-register weights, CUDA graph) and the
+    persistent warp-per-chain kernel must produce identical bits: accept decisions, log-ratios,
+    final states, samples and local energies."""
+    from gpu_util import make_pair
+    q = _q()
+    r = len(layers) * 2 + 1
+    outs = []
+    for force in ("1", "0"):
+        os.environ["QMC_FORCE_PERSISTENT"] = force      # "1": persistent kernels for sweep and energy
+        os.environ["QMC_SWEEP_PATH"] = "batched"         # "0": batched kernels for sweep and energy
+        try:
+            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 17, layers=layers)
+
+            class GS(q.Sampler):
+                MAX_NUM_SAMPLERS = 10 ** 9
+                SWEEPFACTOR, THERMFACTOR = 1, 1
+            init = (np.random.default_rng(3).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+            smp = GS(gm, shape, r, 2 * S, 1, seed=99, chain_id0=5)     # 2 samples per chain
+            smp.MAX_NUM_SAMPLERS = S
+            smp = type("GS2", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))(
+                gm, shape, r, 2 * S, 1, seed=99, chain_id0=5)
+            smp.feed(initial_states=init)
+            samples = smp.mcmc_op(trace=True)            # > 64 steps: exercises the CUDA-graph blocks + remainder
+            e = q.ising_energy(gm, samples, system_shape=shape, H=1.3)
+            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(),
+                         samples.clone(), e.clone(), smp.acceptance_count, smp.sample_its))
+        finally:
+            os.environ.pop("QMC_FORCE_PERSISTENT", None)
+            os.environ.pop("QMC_SWEEP_PATH", None)
+    a, b = outs
+    assert a[6] == b[6] and a[6] > 64
+    assert torch.equal(a[0], b[0]), "accept decisions differ"
+    assert torch.equal(a[1], b[1]), "log-ratios differ"
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    # energies: same per-site terms, summed in a different grouping (8 chunks vs site order)
+    ea, eb = a[4].cpu().numpy(), b[4].cpu().numpy()
+    assert np.abs(ea - eb).max() <= 2e-6 * np.abs(ea).max(), "local energies differ"
+    assert a[5] == b[5] and 0 < a[5] < a[0].numel()
+
+
 # ----------------------------------------------------------------------------- energy
 @pytest.mark.parametrize("name,kind,shape,kw", CASES[:5], ids=[c[0] for c in CASES[:5]])
 @pytest.mark.parametrize("scale", [1e-2, 1e-1])
