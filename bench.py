@@ -206,10 +206,10 @@ def cpu_baseline(cfg, budget_s=20.0):
     S = 256
     rng = np.random.default_rng(0)
     states = torch.as_tensor((rng.integers(0, 2, (S, Ly, Lx)) * 2 - 1).astype(np.float32))
-    its = 4
+    its = 64
     pos = torch.as_tensor(rng.integers(0, Ly * Lx, (its, S, cfg["flips"])).astype(np.int64))
     u = torch.as_tensor(rng.random((its, S)).astype(np.float32))
-    torch_ref.metropolis_steps(tm, states, pos, u)          # warm-up
+    torch_ref.metropolis_steps(tm, states, pos[:4], u[:4])          # warm-up
     done, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s * 0.7:
         torch_ref.metropolis_steps(tm, states, pos, u)
@@ -302,12 +302,14 @@ def run_cuda(args, cfg, name):
         clocks.start()
     t_start, t_end = ev(), ev()
     sampler._n_accept.zero_()
+    launches0 = _lib.load().qmc_launch_count()
     sync()
     t_start.record()
     marks = [step(True) for _ in range(args.steps)]
     t_end.record()
     sync()
     clk = clocks.stop() if clocks else None
+    gpu_launches = int(_lib.load().qmc_launch_count() - launches0)     # counted by the library itself
     elapsed_ms = t_start.elapsed_time(t_end)
     for (e0, e1, e2, e3), _ in marks:
         seg["sweep"] += e0.elapsed_time(e1)
@@ -384,7 +386,8 @@ def run_cuda(args, cfg, name):
         prof = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
         if os.path.exists(prof):
             try:
-                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                roofline["traffic"] = json.load(open(prof))["dram_bytes_per_proposal"] * props_per_launch
+                roofline["traffic_source"] = "profiles/r01_sweep_traffic.json (ncu dram__bytes per proposal x proposals per launch)"
             except Exception:
                 pass
         line = {
@@ -405,7 +408,7 @@ def run_cuda(args, cfg, name):
             "e2e": {"value": e2e_value, "unit": "proposals/s",
                     "h2d_bytes_per_step": S * n + params_host.numel() * 4,
                     "d2h_bytes_per_step": S * n + S * 8, "steps": e2e_steps},
-            "gpu_launches": args.steps * 9,     # forward, sweep | forward, energy, finish | forward, backward, reduce | (+ torch glue)
+            "gpu_launches": gpu_launches,       # this library's kernels in the timed region (qmc_launch_count)
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -426,7 +429,7 @@ def main():
     ap.add_argument("--sweep-its", type=int, default=0, help="Metropolis iterations per step (default sample_its)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-chains", type=int, default=256)
-    ap.add_argument("--ref-its", type=int, default=64)
+    ap.add_argument("--ref-its", type=int, default=256)
     ap.add_argument("--ref-energy", type=int, default=4)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -137,6 +137,10 @@ int qmc_diag_peaks(int device, double* fp32_tflops /*host*/, double* mufu_gops /
 /* same, plus the packed fma.rn.f32x2 (FFMA2) rate in TFLOP/s */
 int qmc_diag_peaks2(int device, double* fp32_tflops, double* ffma2_tflops, double* mufu_gops);
 
+/* number of CUDA kernels this library has launched in this process (graph replays count
+ * their kernel nodes) */
+unsigned long long qmc_launch_count(void);
+
 /* library build info, host string */
 const char* qmc_version(void);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "qmc_logpsi_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_diag_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_diag_peaks2": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "qmc_launch_count": (C.c_ulonglong, []),
     "qmc_version": (C.c_char_p, []),
 }
 

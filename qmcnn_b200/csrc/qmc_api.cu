@@ -6,6 +6,8 @@
 
 using namespace qmc;
 
+namespace qmc { unsigned long long g_launches = 0; }
+
 static thread_local std::string g_create_err;
 
 static int fail(qmc_handle* h, int code, const std::string& msg) {
@@ -62,6 +64,8 @@ static bool build_model(const qmc_model_desc* d, DevModel& m, std::string& err) 
 extern "C" {
 
 const char* qmc_version(void) { return "qmcnn_b200 0.1 (sm_100a)"; }
+
+unsigned long long qmc_launch_count(void) { return qmc::g_launches; }
 
 int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     if (!out || !desc) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "null argument");

@@ -36,6 +36,7 @@ __global__ void k_repack_params(DevModel m, const float* __restrict__ params, fl
 
 cudaError_t repack_params(const qmc_handle* h, cudaStream_t st) {
     const int nthr = 256, nblk = (h->m.smem_param_floats + nthr - 1) / nthr;
+    ++g_launches;
     k_repack_params<<<nblk, nthr, 0, st>>>(h->m, h->d_params, h->d_params_padded);
     return cudaGetLastError();
 }
@@ -211,6 +212,7 @@ cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const floa
     if (smem > h->max_smem) { err = "backward: parameters do not fit in shared memory"; return cudaErrorInvalidValue; }
     e = cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    g_launches += 2;
     k_backward<<<ctas, kBwdThreads, smem, st>>>(m, h->d_params, spins,
                                                reinterpret_cast<const float2*>(weights), N, cache,
                                                gscratch, partial, gplane(m));

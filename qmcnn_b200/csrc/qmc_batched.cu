@@ -470,7 +470,8 @@ static cudaError_t upload_const(const qmc_handle* h, cudaStream_t st) {
                                    cudaMemcpyDeviceToDevice, st);
 }
 
-static cudaError_t enqueue_step(const qmc_handle* h, const BatchArgs& a, int j, cudaStream_t st) {
+static cudaError_t enqueue_step(const qmc_handle* h, const BatchArgs& a, int j, cudaStream_t st, bool count = true) {
+    if (count) g_launches += h->m.D + 1;
     cudaError_t e = launch_first(h, a, j, st);
     for (int l = 1; e == cudaSuccess && l < h->m.D; ++l) e = launch_conv(h, a, l, st);
     if (e == cudaSuccess) e = launch_head(h, a, j, st);
@@ -492,7 +493,7 @@ static cudaError_t run_sweep_part(const qmc_handle* h, BatchArgs a, long long n_
         e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
             cudaError_t e2 = cudaSuccess;
-            for (int j = 0; j < kGraphSteps && e2 == cudaSuccess; ++j) e2 = enqueue_step(h, a, j, st);
+            for (int j = 0; j < kGraphSteps && e2 == cudaSuccess; ++j) e2 = enqueue_step(h, a, j, st, false);
             if (e2 == cudaSuccess) k_b_advance<<<1, 1, 0, st>>>(it_base, kGraphSteps);
             e = cudaStreamEndCapture(st, &graph);
             if (e2 != cudaSuccess) e = e2;
@@ -501,6 +502,7 @@ static cudaError_t run_sweep_part(const qmc_handle* h, BatchArgs a, long long n_
         if (e == cudaSuccess) {
             const long long nblocks = n_steps / kGraphSteps;
             for (long long b = 0; b < nblocks && e == cudaSuccess; ++b) e = cudaGraphLaunch(exec, st);
+            g_launches += (unsigned long long)nblocks * (kGraphSteps * (h->m.D + 1) + 1);
             done = nblocks * kGraphSteps;
         }
         if (exec) cudaGraphExecDestroy(exec);

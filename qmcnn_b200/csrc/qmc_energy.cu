@@ -95,6 +95,7 @@ cudaError_t QMC_CAT(launch_energy_main_w, QMC_MAXW)(const qmc_handle* h, const i
                                                     cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(K_ENERGY, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
+    ++g_launches;
     K_ENERGY<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, spins, N, cache, hamiltonian, partial,
                                                     nchunks, pl, h->allow_tiled ? 1 : 0);
     return cudaGetLastError();
@@ -150,6 +151,7 @@ __global__ void k_energy_finish(DevModel m, const int8_t* __restrict__ spins, in
 cudaError_t launch_energy_finish(const qmc_handle* h, const int8_t* spins, int N, int hamiltonian, float field_h,
                                  const float2* partial, int nchunks, float* e_loc, double* moments,
                                  cudaStream_t st) {
+    ++g_launches;
     k_energy_finish<<<(N + 127) / 128, 128, 0, st>>>(h->m, spins, N, hamiltonian, field_h, partial, nchunks,
                                                     reinterpret_cast<float2*>(e_loc), moments);
     return cudaGetLastError();

@@ -136,6 +136,7 @@ cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, floa
     cudaError_t e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int grid = N < h->num_sms * 4 ? N : h->num_sms * 4;
+    ++g_launches;
     k_forward<<<grid, warps * 32, smem, st>>>(m, h->d_params, spins, N, cache,
                                              reinterpret_cast<float2*>(factors),
                                              reinterpret_cast<float2*>(logpsi), bin, bout, h->allow_tiled ? 1 : 0);

@@ -24,6 +24,9 @@ struct qmc_handle {
 
 namespace qmc {
 
+// number of kernels this library has launched (bench.py's gpu_launches evidence)
+extern unsigned long long g_launches;
+
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 
 // shared-memory plan of warp_eval_flip for boxes up to h0max x w0max

@@ -132,30 +132,20 @@ class OptimizeStep(object):
         self.optimizer = AdamTF1(model.flat, learning_rate)
         self.group = group
         self.last_grad = None
-
-    def _world(self):
-        import torch.distributed as dist
-        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        self.last_energy = None
 
     def run(self, new_samples=None):
-        import torch.distributed as dist
+        from . import distributed as D
         if new_samples is not None:
             self.sampler.new_samples = bool(new_samples)
         self.sampler.mcmc_op()
         samples = self.sampler.samples_int8()
         energies = self.energy_fn(samples)
-        n_local = energies.shape[0]
-        world = self._world()
-        mom = torch.stack([torch.tensor(float(n_local), device=energies.device, dtype=torch.float64),
-                           energies.real.double().sum(), energies.imag.double().sum()])
-        if world > 1:
-            dist.all_reduce(mom, group=self.group)                 # collective 1: energy moments
-        n_tot = mom[0]
-        e_mean = torch.complex(mom[1] / n_tot, mom[2] / n_tot).to(torch.complex64)
-        weights = (energies - e_mean) / n_tot.to(torch.float32)
+        n_tot, e_mean, _, stderr = D.allreduce_energy_moments(energies, self.group)   # collective 1
+        self.last_energy = (e_mean, stderr)
+        weights = D.vmc_weights(energies, e_mean, n_tot)
         grad = logpsi_gradient(self.model, samples, weights, self.sampler.system_shape)
-        if world > 1:
-            dist.all_reduce(grad, group=self.group)                # collective 2: gradient
+        D.allreduce_gradient(grad, self.group)                                        # collective 2
         self.last_grad = grad
         self.optimizer.step(grad)
         return energies
