@@ -115,6 +115,22 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
                          int64_t n_sample_slots, uint8_t* accept_trace, float* logratio_trace,
                          unsigned long long* n_accept, void* stream);
 
+/* Symmetry-averaged amplitude psi_sym(s) = (1/nsym) sum_g psi(s; W o g), g in D4
+ * (symmetry.ipynb cell 0 defines the group; SURVEY.md section 8 the amplitude - the reference
+ * has no amplitude code).  params_images [nsym, P]: the flat parameter vector of every image
+ * (filters of every layer rotated / mirrored, biases unchanged), nsym <= 8. */
+int qmc_set_image_params(qmc_handle* h, int nsym, const float* params_images, void* stream);
+size_t qmc_sym_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips, int nsym);
+/* qmc_metropolis_sweep for |psi_sym|^2.  caches [nsym, S, qmc_cache_floats] (forward of `spins`
+ * under each image), log_rel [S, nsym, 2] fp64 in/out = log psi_g - log psi_0 (Re, Im);
+ * logratio_trace receives log|psi_sym(s')/psi_sym(s)|.  Other arguments as qmc_metropolis_sweep. */
+int qmc_metropolis_sweep_sym(qmc_handle* h, int nsym, int8_t* spins, float* caches, double* log_rel,
+                             float* workspace, int S, int num_flips, int64_t step0, int64_t n_steps,
+                             const int32_t* flip_pos, const float* uniforms, uint64_t seed,
+                             int64_t chain_id0, int64_t therm_its, int64_t its_per_sample,
+                             int8_t* samples, int64_t n_sample_slots, uint8_t* accept_trace,
+                             float* logratio_trace, unsigned long long* n_accept, void* stream);
+
 /* ising_energy / heisenberg_energy (mcmc_tf.py:59-90, 93-141): local energy
  * PER SPIN of N samples; all Ly*Lx (TFIM) or 2*Ly*Lx (Heisenberg) connected
  * configurations evaluated as receptive-field deltas in one launch sequence.

@@ -12,11 +12,12 @@ from .helpers import (create_index_matrix, scope_op, pad, unpad, all_windows, ga
                       update_windows, interactions)
 from .models import CRBM, DCRBM
 from .sampler import Sampler
-from . import distributed
+from . import distributed, symmetry
+from .symmetry import SymmetrizedModel
 from .mcmc import (ising_energy, heisenberg_energy, batched_op, loss_op, optimize_op, eval_op,
                    logpsi_gradient, AdamTF1, OptimizeStep)
 
 __all__ = ["QmcError", "load_library", "LIB_PATH", "create_index_matrix", "scope_op", "pad", "unpad",
            "all_windows", "gather_windows", "update_windows", "interactions", "CRBM", "DCRBM",
-           "Sampler", "distributed", "ising_energy", "heisenberg_energy", "batched_op", "loss_op", "optimize_op",
+           "Sampler", "SymmetrizedModel", "symmetry", "distributed", "ising_energy", "heisenberg_energy", "batched_op", "loss_op", "optimize_op",
            "eval_op", "logpsi_gradient", "AdamTF1", "OptimizeStep"]

@@ -43,6 +43,10 @@ SIGNATURES = {
     "qmc_logpsi_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "qmc_metropolis_sweep": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,
                                   _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "qmc_set_image_params": (_i, [_vp, _i, _vp, _vp]),
+    "qmc_sym_sweep_workspace_floats": (_sz, [_vp, _i, _i, _i]),
+    "qmc_metropolis_sweep_sym": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,
+                                      _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qmc_local_energy": (_i, [_vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "qmc_logpsi_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_diag_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

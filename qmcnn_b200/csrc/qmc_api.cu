@@ -120,6 +120,7 @@ int qmc_destroy(qmc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_params);
     cudaFree(h->d_params_padded);
+    cudaFree(h->d_sym_padded);
     for (int i = 0; i < 2; ++i) {
         if (h->side_stream[i]) cudaStreamDestroy(h->side_stream[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
@@ -236,6 +237,65 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
                             ? launch_sweep_batched(h, a, (cudaStream_t)stream, h->err)
                             : launch_sweep(h, a, (cudaStream_t)stream, h->err);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_set_image_params(qmc_handle* h, int nsym, const float* params_images, void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (nsym < 1 || nsym > 8 || !params_images) rc = fail(h, QMC_ERR_BAD_ARGUMENT, "set_image_params: nsym must be 1..8");
+    else {
+        cudaError_t e = cudaSuccess;
+        if (h->nsym != nsym) {
+            cudaFree(h->d_sym_padded);
+            h->d_sym_padded = nullptr;
+            e = cudaMalloc(&h->d_sym_padded, sizeof(float) * (size_t)nsym * h->m.smem_param_floats);
+            h->nsym = e == cudaSuccess ? nsym : 0;
+        }
+        for (int g = 0; g < nsym && e == cudaSuccess; ++g)
+            e = repack_params_to(h, params_images + (size_t)g * h->m.P,
+                                 h->d_sym_padded + (size_t)g * h->m.smem_param_floats, (cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "set_image_params");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+size_t qmc_sym_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips, int nsym) {
+    if (!h || S < 1) return 0;
+    EvalPlan pl;
+    const int slots = sweep_sym_slots(h, S, num_flips, nsym, &pl, nullptr);
+    if (slots < 0) return 0;
+    const size_t f = (size_t)slots * nsym * pl.staging_floats;
+    return f ? f : 4;
+}
+
+int qmc_metropolis_sweep_sym(qmc_handle* h, int nsym, int8_t* spins, float* caches, double* log_rel,
+                             float* workspace, int S, int num_flips, int64_t step0, int64_t n_steps,
+                             const int32_t* flip_pos, const float* uniforms, uint64_t seed, int64_t chain_id0,
+                             int64_t therm_its, int64_t its_per_sample, int8_t* samples, int64_t n_sample_slots,
+                             uint8_t* accept_trace, float* logratio_trace, unsigned long long* n_accept,
+                             void* stream) {
+    QMC_ENTER(h);
+    int rc = QMC_OK;
+    if (S < 0 || n_steps < 0 || (S > 0 && (!spins || !caches || !workspace || !log_rel)))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep_sym: null argument");
+    else if (nsym != h->nsym || !h->d_sym_padded)
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep_sym: call qmc_set_image_params with the same nsym first");
+    else if (num_flips < 1 || num_flips > QMC_MAX_FLIPS)
+        rc = fail(h, QMC_ERR_UNSUPPORTED, "sweep_sym: num_flips must be 1 or 2");
+    else if ((flip_pos == nullptr) != (uniforms == nullptr))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep_sym: flip_pos and uniforms must both be given or both be NULL");
+    else if (samples && (its_per_sample < 1 || n_sample_slots < 1))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "sweep_sym: its_per_sample and n_sample_slots must be positive");
+    else if (S > 0 && n_steps > 0) {
+        SweepArgs a{spins, caches, workspace, S, num_flips, step0, n_steps, flip_pos, uniforms,
+                    seed, chain_id0, therm_its, its_per_sample > 0 ? its_per_sample : 1, samples,
+                    n_sample_slots, accept_trace, logratio_trace, n_accept};
+        cudaError_t e = launch_sweep_sym(h, a, nsym, log_rel, (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep_sym");
     }
     QMC_LEAVE(h);
     return rc;

@@ -34,11 +34,15 @@ __global__ void k_repack_params(DevModel m, const float* __restrict__ params, fl
     padded[i] = v;
 }
 
-cudaError_t repack_params(const qmc_handle* h, cudaStream_t st) {
+cudaError_t repack_params_to(const qmc_handle* h, const float* flat, float* padded, cudaStream_t st) {
     const int nthr = 256, nblk = (h->m.smem_param_floats + nthr - 1) / nthr;
     ++g_launches;
-    k_repack_params<<<nblk, nthr, 0, st>>>(h->m, h->d_params, h->d_params_padded);
+    k_repack_params<<<nblk, nthr, 0, st>>>(h->m, flat, padded);
     return cudaGetLastError();
+}
+
+cudaError_t repack_params(const qmc_handle* h, cudaStream_t st) {
+    return repack_params_to(h, h->d_params, h->d_params_padded, st);
 }
 
 constexpr int kBwdThreads = 256;

@@ -11,6 +11,8 @@ struct qmc_handle {
     qmc::DevModel m{};
     float* d_params = nullptr;         // caller's flat order
     float* d_params_padded = nullptr;  // padded block layout (shared / constant memory image)
+    float* d_sym_padded = nullptr;     // [nsym] padded blocks of the symmetry images (qmc_set_image_params)
+    int nsym = 0;
     std::string err;
     int num_sms = 0;
     size_t max_smem = 0;   // opt-in dynamic shared memory per CTA
@@ -119,6 +121,10 @@ cudaError_t repack_params(const qmc_handle* h, cudaStream_t st);
 cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
                            float* factors, float* logpsi, cudaStream_t st, std::string& err);
 cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
+cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, double* drel, cudaStream_t st,
+                             std::string& err);
+int sweep_sym_slots(const qmc_handle* h, int S, int num_flips, int nsym, EvalPlan* plan, WarpGrid* grid);
+cudaError_t repack_params_to(const qmc_handle* h, const float* flat, float* padded, cudaStream_t st);
 cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins,
                           int N, float* workspace, float* e_loc, double* moments, cudaStream_t st,
                           std::string& err);

@@ -160,6 +160,179 @@ cudaError_t QMC_CAT(launch_sweep_w, QMC_MAXW)(const qmc_handle* h, const SweepAr
     return cudaGetLastError();
 }
 
+#if QMC_MAXW == 16
+// ------------------------------------------------------------------------------------------
+// Symmetric sweep: Metropolis sampling of |psi_sym|^2, psi_sym = (1/nsym) sum_g psi(.; W o g)
+// (BASELINE config 4; SURVEY.md section 8 defines the amplitude, symmetry.ipynb the group).
+// The warp evaluates the proposal against every image with the same warp_eval_flip (its own
+// parameter block, cache, staging and new-factor buffer per image) and accepts with
+//   |sum_g exp(D_g + delta_g) / sum_g exp(D_g)|^2 > u,   D_g = log psi_g - log psi_0 (double).
+// Generic conv only (the models this is used with are small), 16-warp variant only.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+k_sweep_sym(DevModel m, const float* __restrict__ sym_padded, SweepArgs a, EvalPlan pl, int nsym,
+            double* __restrict__ drel_all) {
+    extern __shared__ float4 smem4[];
+    float* smem_f = reinterpret_cast<float*>(smem4);
+    const int pb = m.smem_param_floats;
+    for (int i = threadIdx.x; i < nsym * pb; i += blockDim.x) smem_f[i] = sym_padded[i];
+    __syncthreads();
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    char* wmem = reinterpret_cast<char*>(smem_f + nsym * pb) + (size_t)warp * pl.per_warp_bytes;
+    float* buf0 = reinterpret_cast<float*>(wmem);
+    float* buf1 = buf0 + pl.buf_floats[0];
+    float* newf = buf1 + pl.buf_floats[1];                      // nsym x (Re, Im) x nfstride
+    int8_t* spins_s = reinterpret_cast<int8_t*>(newf + nsym * pl.newf_floats);
+    const int n = m.n, p = m.p, Ly = m.Ly, Lx = m.Lx;
+    const int slot = blockIdx.x * nwarps + warp, nslots = gridDim.x * nwarps;
+    float* staging0 = a.staging + (size_t)slot * nsym * pl.staging_floats;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const size_t cache_img = (size_t)a.S * m.cache_floats;     // stride between image caches
+    unsigned long long accepted = 0;
+    for (int chain = slot; chain < a.S; chain += nslots) {
+        int8_t* gspins = a.spins + (size_t)chain * n;
+        double* drel = drel_all + (size_t)chain * nsym * 2;
+        for (int i = lane; i < n; i += kWarp) spins_s[i] = gspins[i];
+        __syncwarp();
+        const unsigned long long gchain = (unsigned long long)(a.chain_id0 + chain);
+        for (long long it = 0; it < a.n_steps; ++it) {
+            const long long step = a.step0 + it;
+            int f0, f1 = -1;
+            float u;
+            if (a.flip_pos) {
+                const int32_t* fp = a.flip_pos + ((size_t)it * a.S + chain) * a.num_flips;
+                f0 = fp[0];
+                if (a.num_flips > 1) f1 = fp[1];
+                u = a.uniforms[(size_t)it * a.S + chain];
+            } else {
+                const uint4 r = philox4x32_10(
+                    make_uint4((uint32_t)step, (uint32_t)((unsigned long long)step >> 32),
+                               (uint32_t)gchain, (uint32_t)(gchain >> 32)), key);
+                f0 = (int)__umulhi(r.x, (uint32_t)n);
+                if (a.num_flips > 1) f1 = (int)__umulhi(r.y, (uint32_t)n);
+                u = (float)(r.w >> 8) * 5.9604644775390625e-8f;
+            }
+            bool accept;
+            float lr = 0.f;
+            if (a.num_flips > 1 && f0 == f1) {
+                accept = 1.0f > u;
+            } else {
+                const FlipBox box = make_box(m, a.num_flips, f0, f1);
+                Region reg;
+                double nre = 0, nim = 0, dre_ = 0, dim_ = 0, dl_re[8], dl_im[8];
+                for (int g = 0; g < nsym; ++g) {
+                    float dre, dim;
+                    warp_eval_flip<true, false, false>(m, smem_f + g * pb, buf0, buf1, spins_s,
+                                                       a.cache + g * cache_img + (size_t)chain * m.cache_floats,
+                                                       staging0 + (size_t)g * pl.staging_floats,
+                                                       newf + g * pl.newf_floats, pl.nfstride, box, lane, 0, reg,
+                                                       dre, dim);
+                    dl_re[g] = dre; dl_im[g] = dim;
+                    // weights exp(D_g) are normalised by exp(max Re D) implicitly: D_0 = 0 and the
+                    // images differ by O(1), so plain exp in double is safe
+                    const double wr = exp(drel[2 * g]), wi = drel[2 * g + 1];
+                    const double cr = wr * cos(wi), ci = wr * sin(wi);
+                    dre_ += cr; dim_ += ci;
+                    const double er = exp((double)dre), ei = (double)dim;
+                    const double rr = er * cos(ei), ri = er * sin(ei);
+                    nre += cr * rr - ci * ri;
+                    nim += cr * ri + ci * rr;
+                }
+                const double den = dre_ * dre_ + dim_ * dim_;
+                const double prob = (nre * nre + nim * nim) / den;      // |psi_sym(s') / psi_sym(s)|^2
+                lr = (float)(0.5 * log(prob));
+                accept = __shfl_sync(0xffffffffu, (int)((float)prob > u), 0) != 0;
+                if (accept) {
+                    for (int g = 0; g < nsym; ++g) {
+                        float* cache = a.cache + g * cache_img + (size_t)chain * m.cache_floats;
+                        const float* stg_g = staging0 + (size_t)g * pl.staging_floats;
+                        const float* nf = newf + g * pl.newf_floats;
+                        int rh = box.h0 + 2 * p, rw = box.w0 + 2 * p;
+                        if (rh > Ly) rh = Ly;
+                        if (rw > Lx) rw = Lx;
+                        int ry = box.y0 - p, rx = box.x0 - p, stg = 0;
+                        for (int l = 0; l < m.D - 1; ++l) {
+                            const LayerInfo& L = m.layer[l];
+                            const int rarea = rh * rw, ncg = L.coutp >> 2;
+                            float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
+                            for (int idx = lane; idx < ncg * rarea; idx += kWarp) {
+                                const int cg = idx / rarea, pos = idx - cg * rarea;
+                                const int y = pos / rw, x = pos - y * rw;
+                                plane4[cg * n + wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx)] =
+                                    ldcg4(stg_g + stg + (size_t)idx * 4);
+                            }
+                            stg += L.coutp * rarea;
+                            ry -= p; rx -= p; rh += 2 * p; rw += 2 * p;
+                        }
+                        for (int pos = lane; pos < reg.rh * reg.rw; pos += kWarp) {
+                            const int y = pos / reg.rw, x = pos - y * reg.rw;
+                            const int site = wrap1(reg.ry + y, Ly) * Lx + wrap1(reg.rx + x, Lx);
+                            cache[m.fre_off + site] = nf[pos];
+                            cache[m.fim_off + site] = nf[pl.nfstride + pos];
+                        }
+                    }
+                    if (lane == 0) {
+                        for (int g = 1; g < nsym; ++g) {       // D_g += delta_g - delta_0
+                            drel[2 * g] += dl_re[g] - dl_re[0];
+                            drel[2 * g + 1] += dl_im[g] - dl_im[0];
+                        }
+                        spins_s[f0] = -spins_s[f0];
+                        if (a.num_flips > 1) spins_s[f1] = -spins_s[f1];
+                    }
+                    __syncwarp();
+                }
+            }
+            if (accept) ++accepted;
+            if (lane == 0) {
+                if (a.accept_trace) a.accept_trace[(size_t)it * a.S + chain] = accept ? 1 : 0;
+                if (a.logratio_trace) a.logratio_trace[(size_t)it * a.S + chain] = lr;
+            }
+            if (a.samples && step >= a.therm_its && (step - a.therm_its) % a.its_per_sample == 0) {
+                const long long j = (step - a.therm_its) / a.its_per_sample;
+                if (j < a.n_sample_slots) {
+                    int8_t* dst = a.samples + ((size_t)j * a.S + chain) * n;
+                    for (int i = lane; i < n; i += kWarp) dst[i] = spins_s[i];
+                }
+            }
+        }
+        for (int i = lane; i < n; i += kWarp) gspins[i] = spins_s[i];
+        __syncwarp();
+    }
+    if (a.n_accept && lane == 0 && accepted) atomicAdd(a.n_accept, accepted);
+}
+
+int sweep_sym_slots(const qmc_handle* h, int S, int num_flips, int nsym, EvalPlan* plan, WarpGrid* grid) {
+    const DevModel& m = h->m;
+    if (nsym < 1 || nsym > 8) return -3;
+    int h0 = 1, w0 = 1;
+    if (num_flips > 1) { h0 = m.Ly / 2 + 1; w0 = m.Lx / 2 + 1; }
+    if (!box_supported(m, h0, w0)) return -1;
+    EvalPlan pl = eval_plan(m, h0, w0, true);
+    const size_t per_warp = pl.per_warp_bytes + (size_t)(nsym - 1) * pl.newf_floats * 4;
+    const size_t extra_params = (size_t)(nsym - 1) * m.smem_param_floats * 4;
+    WarpGrid g = pick_warp_grid(h, per_warp, extra_params, S);
+    if (!g.ok) return -2;
+    pl.per_warp_bytes = per_warp;
+    if (plan) *plan = pl;
+    if (grid) *grid = g;
+    return g.grid * g.warps;
+}
+
+cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, double* drel, cudaStream_t st,
+                             std::string& err) {
+    EvalPlan pl; WarpGrid g;
+    const int slots = sweep_sym_slots(h, a.S, a.num_flips, nsym, &pl, &g);
+    if (slots == -1) { err = "sweep_sym: flip box does not fit the lattice"; return cudaErrorInvalidValue; }
+    if (slots < 0) { err = "sweep_sym: nsym images of the model do not fit in shared memory"; return cudaErrorInvalidValue; }
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    ++g_launches;
+    k_sweep_sym<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_sym_padded, a, pl, nsym, drel);
+    return cudaGetLastError();
+}
+#endif
+
 #if QMC_MAXW == 8
 cudaError_t launch_sweep_w16(const qmc_handle* h, const SweepArgs& a, const EvalPlan& pl,
                              const WarpGrid& g, cudaStream_t st);

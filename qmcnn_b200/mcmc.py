@@ -30,7 +30,16 @@ def _prep(model, states, system_shape):
     return states.contiguous(), system_shape, model.handle(system_shape)
 
 
+def _is_sym(model):
+    from .symmetry import SymmetrizedModel
+    return isinstance(model, SymmetrizedModel)
+
+
 def _local_energy(model, states, system_shape, hamiltonian, h_field, moments=None):
+    if _is_sym(model):     # E_loc[psi_sym] = sum_g p_g E_loc[psi_g]
+        shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
+        fn = lambda im, st, system_shape: _local_energy(im, st, system_shape, hamiltonian, h_field)
+        return model.local_energy(fn, states, shape)
     states, system_shape, h = _prep(model, states, system_shape)
     N = states.shape[0]
     out = torch.empty(N, dtype=torch.complex64, device=model.device)
@@ -89,6 +98,13 @@ def loss_op(factors, energies):
 def logpsi_gradient(model, states, weights, system_shape=None, out=None):
     """sum_n Re[w_n conj(d log psi_n / d p)] as a flat fp32 vector in ``model.flat`` order.
     With w_n = (E_n - mean E)/N this is d loss_op / d p (``mcmc_tf.py:172-177``)."""
+    if _is_sym(model):
+        shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
+        g = model.gradient(lambda im, st, w, sh: logpsi_gradient(im, st, w, sh), states, weights, shape)
+        if out is not None:
+            out.add_(g)
+            return out
+        return g
     states, system_shape, h = _prep(model, states, system_shape)
     N = states.shape[0]
     grad = torch.zeros(model.num_params, dtype=torch.float32, device=model.device) if out is None else out

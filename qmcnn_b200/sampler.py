@@ -54,9 +54,16 @@ class Sampler(object):
         S, n = self.num_samplers, self.num_spins
         self._h = model.handle(self.system_shape)
         lib = _lib.load()
+        from .symmetry import SymmetrizedModel
+        self._sym = isinstance(model, SymmetrizedModel)
+        nimg = model.NSYM if self._sym else 1
         self._spins = torch.zeros((S, n), dtype=torch.int8, device=self.device)
-        self._cache = torch.zeros(S * self._h.cache_floats, dtype=torch.float32, device=self.device)
-        ws = lib.qmc_sweep_workspace_floats(self._h.ptr, S, num_flips)
+        self._cache = torch.zeros(nimg * S * self._h.cache_floats, dtype=torch.float32, device=self.device)
+        if self._sym:
+            self._log_rel = torch.zeros((S, nimg, 2), dtype=torch.float64, device=self.device)
+            ws = lib.qmc_sym_sweep_workspace_floats(self._h.ptr, S, num_flips, nimg)
+        else:
+            ws = lib.qmc_sweep_workspace_floats(self._h.ptr, S, num_flips)
         if ws == 0:
             raise _lib.QmcError("Sampler: this model / lattice / num_flips combination is outside the "
                                 "incremental sweep's coverage (needs bounding box + r - 1 <= L)")
@@ -83,7 +90,8 @@ class Sampler(object):
     @property
     def current_factors_var(self):
         """complex64 [S, num_spins] (sampler.py:49-53), recomputed from the spins."""
-        return self.model.forward_unpadded(self._spins, self.system_shape)[0]
+        m = self.model.base if self._sym else self.model
+        return m.forward_unpadded(self._spins, self.system_shape)[0]
 
     @property
     def samples_var(self):
@@ -123,8 +131,21 @@ class Sampler(object):
             else:
                 self._spins.copy_(torch.randint(0, 2, self._spins.shape, generator=self._gen,
                                                 device=self.device, dtype=torch.int8) * 2 - 1)
-        self.model.forward_unpadded(self._spins, self.system_shape, want_factors=False,
-                                    cache=self._cache)
+        if self._sym:
+            # caches of the 8 images + relative log amplitudes from per-site factor differences
+            S, cf = self.num_samplers, self._h.cache_floats
+            facs = []
+            for g, im in enumerate(self.model.images()):
+                f, _, _ = im.forward_unpadded(self._spins, self.system_shape, want_factors=True,
+                                              cache=self._cache[g * S * cf:(g + 1) * S * cf])
+                facs.append(f.to(torch.complex128))
+            for g in range(len(facs)):
+                d = (facs[g] - facs[0]).sum(1)
+                self._log_rel[:, g, 0] = d.real
+                self._log_rel[:, g, 1] = d.imag
+        else:
+            self.model.forward_unpadded(self._spins, self.system_shape, want_factors=False,
+                                        cache=self._cache)
         self._samples.zero_()
 
     def _sweep(self, step0, n_steps, trace=False):
@@ -141,6 +162,21 @@ class Sampler(object):
         if trace:
             self.accept_trace = torch.zeros((n_steps, S), dtype=torch.uint8, device=self.device)
             self.logratio_trace = torch.zeros((n_steps, S), dtype=torch.float32, device=self.device)
+        if self._sym:
+            imgs = self.model.sync().contiguous()
+            lib = _lib.load()
+            _lib.check(h.ptr, lib.qmc_set_image_params(h.ptr, imgs.shape[0], imgs.data_ptr(),
+                                                       _stream_ptr(self.device)), "qmc_set_image_params")
+            _lib.check(h.ptr, lib.qmc_metropolis_sweep_sym(
+                h.ptr, imgs.shape[0], self._spins.data_ptr(), self._cache.data_ptr(), self._log_rel.data_ptr(),
+                self._workspace.data_ptr(), S, self.num_flips, step0 + (0 if fed else self._step_base), n_steps,
+                fp.data_ptr() if fed else None, ua.data_ptr() if fed else None, self.seed, self.chain_id0,
+                self.therm_its + (0 if fed else self._step_base), self.its_per_sample,
+                self._samples.data_ptr(), self.samples_per_sampler,
+                self.accept_trace.data_ptr() if trace else None,
+                self.logratio_trace.data_ptr() if trace else None,
+                self._n_accept.data_ptr(), _stream_ptr(self.device)), "qmc_metropolis_sweep_sym")
+            return
         _lib.check(h.ptr, _lib.load().qmc_metropolis_sweep(
             h.ptr, self._spins.data_ptr(), self._cache.data_ptr(), self._workspace.data_ptr(),
             S, self.num_flips, step0 + (0 if fed else self._step_base), n_steps,

@@ -1,0 +1,96 @@
+"""GPU parity of the symmetry-averaged amplitude (BASELINE config 4: Heisenberg, CRBM(5,2,4,2),
+D4 x| T average) against the oracle's brute-force definitions."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import symmetry as osym
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(kind, L, scale, seed, **kw):
+    from gpu_util import make_pair
+    import qmcnn_b200 as q
+    gm, om = make_pair(kind, L, scale, seed, dtype=np.float64, **kw)
+    return q, q.SymmetrizedModel(gm), om
+
+
+def test_tap_permutations_match_oracle_filter_images():
+    import qmcnn_b200 as q
+    rng = np.random.default_rng(0)
+    for k in (3, 5):
+        W = rng.standard_normal((k, k, 2, 3))
+        perms = q.symmetry.d4_tap_permutations(k)
+        for p, img in enumerate(osym.d4_filter_images(W)):
+            assert np.array_equal(W.reshape(k * k, 2, 3)[perms[p]].reshape(W.shape), img)
+    # the notebook's checks on the product's own group module
+    M = 4
+    G = q.symmetry.group(M)
+    assert len({g.tobytes() for g in G}) == 8 * M * M
+    ident = q.symmetry.neighbours(q.symmetry.plot(q.symmetry.translations(M)[0], M), M)
+    assert all(q.symmetry.neighbours(q.symmetry.plot(g, M), M) == ident for g in G)
+
+
+@pytest.mark.parametrize("kind,L,kw", [("crbm", 6, dict(k=5, alpha=4)), ("dcrbm", 8, dict(k=3, layers=[4, 6, 4]))])
+def test_sym_logpsi_energy_gradient(kind, L, kw):
+    q, sm, om = _pair(kind, L, 2e-1, 41, **kw)
+    shape = (L, L)
+    rng = np.random.default_rng(1)
+    s = (rng.integers(0, 2, (5, L * L)) * 2 - 1).astype(np.int32)
+    st = torch.as_tensor(s, device="cuda")
+    want = osym.log_mean_exp(osym.log_psi_images(om, s, shape))
+    got = sm.log_psi(st, shape).cpu().numpy()
+    assert np.abs(np.exp(got - want) - 1).max() < 2e-5          # amplitudes agree (phase mod 2 pi)
+    e_t = q.ising_energy(sm, st, system_shape=shape, H=0.8).cpu().numpy()
+    assert np.abs(e_t - osym.sym_local_energy(om, s, shape, "tfim", H=0.8)).max() < 2e-5 * max(1, np.abs(e_t).max())
+    if om.r + 1 <= L:
+        e_h = q.heisenberg_energy(sm, st, system_shape=shape).cpu().numpy()
+        assert np.abs(e_h - osym.sym_local_energy(om, s, shape, "heis")).max() < 2e-5 * max(1, np.abs(e_h).max())
+    # gradient of sum_n Re[w_n conj(log psi_sym,n)] against finite differences of the oracle
+    w = (rng.standard_normal(5) + 1j * rng.standard_normal(5)) / 5
+    g = q.logpsi_gradient(sm, st, torch.as_tensor(w.astype(np.complex64), device="cuda"), shape).cpu().numpy()
+    flat = om.flat_params().copy()
+    f = lambda: float(np.real((w * np.conj(osym.log_mean_exp(osym.log_psi_images(om, s, shape)))).sum()))
+    for i in rng.choice(flat.size, 10, replace=False):
+        d = np.zeros_like(flat); d[i] = 1e-5
+        om.set_flat_params(flat + d); fp = f()
+        om.set_flat_params(flat - d); fm = f()
+        assert abs((fp - fm) / 2e-5 - g[i]) < 2e-4 * max(1.0, np.abs(g).max()), i
+    om.set_flat_params(flat)
+
+
+@pytest.mark.parametrize("num_flips", [1, 2])
+def test_sym_sweep_lockstep(num_flips):
+    """C4-like: 6x6, CRBM, symmetric Metropolis sweep vs the oracle's brute-force psi_sym sampler."""
+    q, sm, om = _pair("crbm", 6, 3e-1, 43, k=3, alpha=3)
+    shape, S, n_steps = (6, 6), 20, 120
+    rng = np.random.default_rng(2)
+    init = (rng.integers(0, 2, (S, 36)) * 2 - 1).astype(np.int32)
+    pos = rng.integers(0, 36, (n_steps, S, num_flips)).astype(np.int32)
+    u = rng.random((n_steps, S)).astype(np.float32)
+    if num_flips == 2:
+        pos[2, 1] = pos[2, 1, 0]
+    smp = q.Sampler(sm, shape, sm.r, S, num_flips)
+    smp.feed(init, pos, u)
+    smp.mcmc_op(n_its=n_steps, trace=True)
+    acc = smp.accept_trace.cpu().numpy().astype(bool)
+    lr = smp.logratio_trace.cpu().numpy()
+    osmp = osym.SymSampler(om, shape, num_flips)
+    osmp.reset(init)
+    ties, err = 0, 0.0
+    for i in range(n_steps):
+        osmp.step(pos[i], u[i], force_mask=acc[i])
+        t = osmp.last_log_ratio.real
+        if num_flips == 2:
+            t = np.where(pos[i, :, 0] == pos[i, :, 1], 0.0, t)
+        err = max(err, float((np.abs(lr[i] - t) / np.maximum(1, np.abs(t))).max()))
+        for c in np.nonzero(osmp.last_own_mask != acc[i])[0]:
+            assert abs(2 * t[c] - np.log(max(float(u[i, c]), 1e-45))) < 1e-4, (i, c)
+            ties += 1
+    assert err < 2e-5 and ties <= 2
+    assert np.array_equal(smp.spins.cpu().numpy().astype(np.int32), osmp.states)
+    assert 0.05 < acc.mean() < 0.99
+    if num_flips == 2:
+        assert acc[2, 1]

@@ -375,3 +375,41 @@ def test_adam_tf1_first_step():
     p, m, v = oracle.adam_tf1_step(np.array([1.0]), np.array([0.5]), 0.0, 0.0, 1, lr=0.1)
     # m = 0.05, v = 2.5e-4, lr_t = 0.1*sqrt(1e-3)/0.1
     assert np.allclose(p, 1.0 - np.sqrt(1e-3) * 0.05 / (np.sqrt(2.5e-4) + 1e-8))
+
+
+# symmetry-averaged amplitude ------------------------------------------------------------
+def test_symmetrised_amplitude_definitions_agree():
+    """8 filter images == 8 point-group images of the state == full 8 L^2 group average;
+    psi_sym is invariant under every group element; for a deep model too."""
+    L = 6
+    rng = np.random.default_rng(31)
+    s = _states(rng, 3, L)
+    for model in (oracle.CRBM(5, 2, 3, 2, rng=rng, scale=0.2, dtype=np.float64),
+                  oracle.DCRBM(3, [3, 4], 2, rng=rng, scale=0.3, dtype=np.float64)):
+        a = sym.log_mean_exp(sym.log_psi_images(model, s, (L, L)))
+        b = sym.symmetrised_log_psi(model, s, (L, L), full_group=False)
+        c = sym.symmetrised_log_psi(model, s, (L, L), full_group=True)
+        assert np.abs(np.exp(a - b) - 1).max() < 1e-12 and np.abs(np.exp(a - c) - 1).max() < 1e-12
+        for g in sym.group(L)[::37]:
+            gs = s[:, sym.site_permutation(g, L)]
+            a2 = sym.log_mean_exp(sym.log_psi_images(model, gs, (L, L)))
+            assert np.abs(np.exp(a2 - a) - 1).max() < 1e-12
+
+
+def test_symmetrised_local_energy_is_weighted_image_energy():
+    """E_loc[psi_sym] = sum_g p_g E_loc[psi_g], p_g = psi_g / sum psi_g - the identity the CUDA path uses."""
+    L = 6
+    rng = np.random.default_rng(32)
+    model = oracle.CRBM(3, 1, 2, 2, rng=rng, scale=0.3, dtype=np.float64)
+    s = _states(rng, 4, L)
+    logs = sym.log_psi_images(model, s, (L, L))
+    p = np.exp(logs - logs.real.max(0))
+    p = p / p.sum(0)
+    for ham in ("tfim", "heis"):
+        want = sym.sym_local_energy(model, s, (L, L), ham, H=0.7)
+        imgs = sym.image_models(model)
+        if ham == "tfim":
+            eg = np.stack([oracle.ising_energy(m, s, (L, L), 3, H=0.7) for m in imgs], 0)
+        else:
+            eg = np.stack([oracle.heisenberg_energy(m, s, (L, L), 3) for m in imgs], 0)
+        assert np.abs((p * eg).sum(0) - want).max() < 1e-10
