@@ -42,6 +42,8 @@ CONFIGS = {
     "C2": dict(shape=(10, 10), kind="dcrbm", k=3, layers=[8, 8, 8], chains=4096, H=3.0, ham="tfim", flips=1),
     "C3": dict(shape=(20, 20), kind="dcrbm", k=3, layers=[16, 16, 16, 16, 16, 8], chains=4096, H=1.0,
                ham="tfim", flips=1),
+    # tuning experiment (not a BASELINE config): 4-layer variant whose tiles allow 14+ warps per SM
+    "X4": dict(shape=(20, 20), kind="dcrbm", k=3, layers=[16, 16, 16, 8], chains=4096, H=1.0, ham="tfim", flips=1),
     "C4": dict(shape=(10, 10), kind="crbm", k=5, alpha=4, chains=8192, H=1.0, ham="heis", flips=2, sym=True),
     "C5": dict(shape=(40, 40), kind="dcrbm", k=3, layers=[16, 16, 16, 16, 16, 8], chains=8192, H=1.0,
                ham="tfim", flips=1),

@@ -95,6 +95,10 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     if (e == cudaSuccess) e = cudaMemset(h->d_params_padded, 0, sizeof(float) * (size_t)m.smem_param_floats);
     const char* fp = std::getenv("QMC_FORCE_PERSISTENT");
     h->allow_batched = !(fp && fp[0] == '1');
+    const char* nl = std::getenv("QMC_LEAN");      // opt-in: measured slower than the classic kernel
+    h->allow_lean = nl && nl[0] == '1';
+    const char* mw = std::getenv("QMC_MAX_WARPS");
+    h->max_warps_override = mw ? std::atoi(mw) : 0;
     const char* sp = std::getenv("QMC_SWEEP_PATH");
     h->batched_sweep = h->allow_batched && sp && std::strcmp(sp, "batched") == 0;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -143,6 +147,13 @@ size_t qmc_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips) {
     const int slots = sweep_slots(h, S, num_flips, &pl, nullptr);
     if (slots < 0) return 0;
     size_t f = (size_t)slots * pl.staging_floats;
+    if (num_flips == 1) {
+        const LeanLaunch ll = lean_launch_plan(h, S);
+        if (ll.ok) {
+            const size_t b = (size_t)ll.grid * ll.warps * ll.staging_floats;
+            if (b > f) f = b;
+        }
+    }
     if (num_flips == 1 && h->batched_sweep && batched_supported(h)) {
         const int half = (S + 1) / 2;     // the chains may be split over two streams, each with its own scratch
         const size_t b = 2 * (batched_staging_floats(h, half) + batched_scratch_floats(half)) + 16;
@@ -233,9 +244,14 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
         SweepArgs a{spins, cache, workspace, S, num_flips, step0, n_steps, flip_pos, uniforms,
                     seed, chain_id0, therm_its, its_per_sample > 0 ? its_per_sample : 1, samples,
                     n_sample_slots, accept_trace, logratio_trace, n_accept};
-        cudaError_t e = (num_flips == 1 && h->batched_sweep && batched_supported(h))
-                            ? launch_sweep_batched(h, a, (cudaStream_t)stream, h->err)
-                            : launch_sweep(h, a, (cudaStream_t)stream, h->err);
+        cudaError_t e;
+        LeanLaunch ll{};
+        if (num_flips == 1 && h->batched_sweep && batched_supported(h))
+            e = launch_sweep_batched(h, a, (cudaStream_t)stream, h->err);
+        else if (num_flips == 1 && (ll = lean_launch_plan(h, S)).ok)
+            e = launch_sweep_lean(h, a, ll, (cudaStream_t)stream);
+        else
+            e = launch_sweep(h, a, (cudaStream_t)stream, h->err);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep");
     }
     QMC_LEAVE(h);

@@ -18,7 +18,7 @@
 
 namespace qmc {
 
-constexpr bool kBig = QMC_MAXW <= 8;
+constexpr int kAcc = QMC_MAXW <= 8 ? 64 : 32;
 
 constexpr int kEnergyChunks = 8;   // site chunks per sample (warp tasks = N * chunks)
 
@@ -61,7 +61,7 @@ K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
             float dre, dim, sn, cn;
             if (hamiltonian == QMC_HAMILTONIAN_TFIM) {
                 const FlipBox box = make_box(m, 1, i, -1);
-                warp_eval_flip<true, kBig>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride, box,
+                warp_eval_flip<true, kAcc>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride, box,
                                      lane, allow_tiled, reg, dre, dim);
                 const float amp = expf(dre);
                 sincosf(dim, &sn, &cn);
@@ -76,7 +76,7 @@ K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
                     const bool aligned = __shfl_sync(0xffffffffu, (int)(spins_s[i] == spins_s[j]), 0) != 0;
                     if (aligned) { are += 1.f; continue; }                   // -(1-1) exp + 1
                     const FlipBox box = make_box(m, 2, i, j);
-                    warp_eval_flip<true, kBig>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride,
+                    warp_eval_flip<true, kAcc>(m, sp, buf0, buf1, spins_s, cache, nullptr, newf, pl.nfstride,
                                          box, lane, allow_tiled, reg, dre, dim);
                     const float amp = expf(dre);
                     sincosf(dim, &sn, &cn);

@@ -64,7 +64,7 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
                 __syncwarp();
                 if (!last) {
                     float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
-                    conv_region<true>(m, l, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
+                    conv_region<64>(m, l, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
                                 [&](int, int y, int x, int cog, float4 a) {
                                     a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
                                     plane4[cog * n + (ry + y) * Lx + rx + x] = a;
@@ -72,7 +72,7 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
                 } else {
                     float4* tout4 = reinterpret_cast<float4*>(tout);
                     const int rarea = rh * rw;
-                    conv_region<true>(m, l, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
+                    conv_region<64>(m, l, sp, tin, tw, tarea, rh, rw, lane, allow_tiled,
                                 [&](int pos, int, int, int cog, float4 a) { tout4[cog * rarea + pos] = a; });
                     __syncwarp();
                     for (int pos = lane; pos < rarea; pos += kWarp) {

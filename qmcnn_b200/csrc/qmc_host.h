@@ -17,6 +17,8 @@ struct qmc_handle {
     int num_sms = 0;
     size_t max_smem = 0;   // opt-in dynamic shared memory per CTA
     bool allow_tiled = true;  // QMC_FORCE_GENERIC=1 disables the specialised conv instances
+    int max_warps_override = 0;  // QMC_MAX_WARPS: tuning knob, caps the warps per CTA of the persistent kernels
+    bool allow_lean = false;     // QMC_LEAN=1: lean persistent sweep kernel (more warps, smaller tiles); off by default
     bool allow_batched = true;  // QMC_FORCE_PERSISTENT=1 disables the layer-synchronous batched path (energy + sweep)
     bool batched_sweep = false; // QMC_SWEEP_PATH=batched: use the batched path for the sweep too (default: persistent
                                 // kernel, which is faster at a few thousand chains per GPU - DESIGN.md)
@@ -77,6 +79,43 @@ inline bool box_supported(const DevModel& m, int h0, int w0) {
     return h0 + 2 * m.D * m.p <= m.Ly && w0 + 2 * m.D * m.p <= m.Lx;
 }
 
+// shared-memory plan of warp_eval_flip_lean for a per-warp arena of at most budget_floats
+inline LeanPlan lean_plan(const DevModel& m, int budget_floats) {
+    LeanPlan best{};
+    best.ok = 0;
+    if (m.D < 2 || m.r > m.Ly || m.r > m.Lx) return best;
+    const int p = m.p;
+    for (int fg = m.D - 1; fg >= 1; --fg) {            // prefer as few gathering layers as possible
+        LeanPlan lp{};
+        lp.first_gather = fg;
+        int bufa = 0, bufb = 0;
+        for (int l = 0; l < fg; ++l) {                 // chained tiles alternate between the two buffers
+            const int tside = 1 + 2 * (l + 1) * p + 2 * p;
+            const int t = tside * tside * m.layer[l].cinp;
+            int& dst = (l & 1) ? bufb : bufa;
+            dst = dst > t ? dst : t;
+        }
+        lp.off_b = round4(bufa);
+        int need = round4(bufa) + round4(bufb);
+        bool ok = need <= budget_floats;
+        for (int l = fg; l < m.D && ok; ++l) {
+            const int side = 1 + 2 * (l + 1) * p, tside = side + 2 * p;
+            const bool last = l == m.D - 1;
+            int nb = 0;
+            for (int b = 1; b <= 4; ++b) {
+                const int rows = (side + b - 1) / b;
+                int t = round4((rows + 2 * p) * tside * m.layer[l].cinp);
+                if (last) t += round4(rows * side * m.layer[l].coutp);
+                if (t <= budget_floats) { nb = b; need = need > t ? need : t; break; }
+            }
+            if (!nb) ok = false;
+            lp.bands[l] = nb;
+        }
+        if (ok) { lp.arena_floats = round4(need); lp.ok = 1; return lp; }
+    }
+    return best;
+}
+
 struct WarpGrid { int grid, warps; size_t smem; bool ok; };
 
 // one CTA per SM, W warps, W chosen to minimise the idle tail over `units` warp tasks
@@ -87,6 +126,7 @@ inline WarpGrid pick_warp_grid(const qmc_handle* h, size_t per_warp_bytes, size_
     if (param_bytes + per_warp_bytes > h->max_smem) return g;
     int wmax = (int)((h->max_smem - param_bytes) / per_warp_bytes);
     if (wmax > max_warps) wmax = max_warps;
+    if (h->max_warps_override > 0 && wmax > h->max_warps_override) wmax = h->max_warps_override;
     int best = wmax;
     double best_eff = -1;
     const int wmin = wmax > 2 ? (wmax + 1) / 2 : 1;
@@ -121,6 +161,9 @@ cudaError_t repack_params(const qmc_handle* h, cudaStream_t st);
 cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
                            float* factors, float* logpsi, cudaStream_t st, std::string& err);
 cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
+struct LeanLaunch { LeanPlan lp; int warps, grid; size_t smem; int newf_floats, spins_bytes, staging_floats; bool ok; };
+LeanLaunch lean_launch_plan(const qmc_handle* h, int S);
+cudaError_t launch_sweep_lean(const qmc_handle* h, const SweepArgs& a, const LeanLaunch& ll, cudaStream_t st);
 cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, double* drel, cudaStream_t st,
                              std::string& err);
 int sweep_sym_slots(const qmc_handle* h, int S, int num_flips, int nsym, EvalPlan* plan, WarpGrid* grid);

@@ -23,7 +23,7 @@ namespace qmc {
 #define QMC_CAT2(a, b) a##b
 #define QMC_CAT(a, b) QMC_CAT2(a, b)
 #define K_SWEEP QMC_CAT(k_sweep_w, QMC_MAXW)
-constexpr bool kBig = QMC_MAXW <= 8;
+constexpr int kAcc = QMC_MAXW <= 8 ? 64 : 32;   // accumulators per lane the register budget allows
 
 __global__ void __launch_bounds__(QMC_MAXW * 32, 1)
 K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, int allow_tiled) {
@@ -83,7 +83,7 @@ K_SWEEP(DevModel m, const float* __restrict__ params, SweepArgs a, EvalPlan pl, 
                 const FlipBox box = make_box(m, a.num_flips, f0, f1);
                 Region reg;
                 float dim;
-                warp_eval_flip<false, kBig>(m, sp, buf0, buf1, spins_s, cache, staging, newf, pl.nfstride,
+                warp_eval_flip<false, kAcc>(m, sp, buf0, buf1, spins_s, cache, staging, newf, pl.nfstride,
                                       box, lane, allow_tiled, reg, dre, dim);
                 const float amp = expf(dre);            // |exp(z)| = exp(Re z)
                 accept = __shfl_sync(0xffffffffu, (int)(amp * amp > u), 0) != 0;   // strict, sampler.py:125
@@ -223,7 +223,7 @@ k_sweep_sym(DevModel m, const float* __restrict__ sym_padded, SweepArgs a, EvalP
                 double nre = 0, nim = 0, dre_ = 0, dim_ = 0, dl_re[8], dl_im[8];
                 for (int g = 0; g < nsym; ++g) {
                     float dre, dim;
-                    warp_eval_flip<true, false, false>(m, smem_f + g * pb, buf0, buf1, spins_s,
+                    warp_eval_flip<true, 32, false>(m, smem_f + g * pb, buf0, buf1, spins_s,
                                                        a.cache + g * cache_img + (size_t)chain * m.cache_floats,
                                                        staging0 + (size_t)g * pl.staging_floats,
                                                        newf + g * pl.newf_floats, pl.nfstride, box, lane, 0, reg,

@@ -295,6 +295,39 @@ def test_batched_path_is_bit_identical_to_persistent(layers, shape, S):
     assert a[5] == b[5] and 0 < a[5] < a[0].numel()
 
 
+@pytest.mark.parametrize("layers,shape,S", [([16, 16, 16, 16, 16, 8], (20, 20), 40), ([8, 8, 8], (10, 10), 50),
+                                            ([3, 5, 6], (9, 8), 17), ([16, 8], (7, 9), 9)])
+def test_lean_kernel_is_bit_identical_to_classic(layers, shape, S):
+    """k_sweep_lean (band-wise re-gathered tiles, 14 warps per SM) against the classic persistent kernel."""
+    from gpu_util import make_pair
+    q = _q()
+    r = len(layers) * 2 + 1
+    outs = []
+    for lean in ("0", "1"):
+        os.environ["QMC_LEAN"] = lean
+        try:
+            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 23, layers=layers)
+            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+            init = (np.random.default_rng(4).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+            smp = GS(gm, shape, r, 2 * S, 1, seed=7, chain_id0=11)
+            smp.feed(initial_states=init)
+            samples = smp.mcmc_op(trace=True)
+            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
+                         smp.current_factors_var.clone(), smp._cache.clone()))
+        finally:
+            os.environ.pop("QMC_LEAN", None)
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert 0 < int(a[0].sum()) < a[0].numel()
+    # the hidden-layer planes and the Re factor plane of the incrementally maintained caches agree bit for bit
+    h = gm.handle(shape)
+    cf, n = h.cache_floats, shape[0] * shape[1]
+    ca, cb = a[5].view(S, cf), b[5].view(S, cf)
+    used = cf - 2 * ((n + 3) // 4 * 4) + n          # everything up to and including fRe
+    assert torch.equal(ca[:, :used], cb[:, :used])
+
+
 # ----------------------------------------------------------------------------- energy
 @pytest.mark.parametrize("name,kind,shape,kw", CASES[:5], ids=[c[0] for c in CASES[:5]])
 @pytest.mark.parametrize("scale", [1e-2, 1e-1])
