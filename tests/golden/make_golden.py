@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN PYTHON, unmodified.
+
+Run in the build container (needs /root/reference, read-only):
+
+    python tests/golden/make_golden.py
+
+The reference (dmaloneynygc/qmcnn: helpers.py, models.py, sampler.py, mcmc_tf.py) is TF-1
+graph-mode code and TensorFlow cannot be installed here.  ``oracle/tf1_shim`` provides the
+55 ``tf.*`` symbols it uses as eager torch-CPU ops, so the four files are imported as they
+lie under /root/reference and their functions are called as a user script would call them.
+``mcmc_tf.py`` ends in a module-level training script (``mcmc_tf.py:197-236``) that needs a
+Session; only the text before ``config = tf.ConfigProto(`` (the function definitions and
+module constants, ``mcmc_tf.py:1-194``) is executed, and the module constants
+(``K, H, SYSTEM_SHAPE, ...``, which the energy functions read as globals) are set per case.
+
+Every case is run twice - tf.float32/complex64 as float32/complex64 ("single", what TF
+computes up to kernel rounding) and carried in float64/complex128 ("double", ground truth)
+- and the generator insists that both runs take identical accept decisions, so the
+recorded Markov chains contain no floating-point near-ties and implementations can be
+asked to reproduce them bit for bit.
+
+Nothing under tests/ or the product reads /root/reference at test time; the committed
+.npz files are the fixtures.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("QMCNN_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "oracle", "tf1_shim"))
+
+import tensorflow as tf  # noqa: E402  (the shim)
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod          # sampler.py / models.py do `from helpers import ...`
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ref_helpers = _load("helpers")
+ref_models = _load("models")
+ref_sampler = _load("sampler")
+
+
+def _load_mcmc_tf():
+    """mcmc_tf.py:1-194 (definitions), without the training script at the bottom."""
+    src = open(os.path.join(REF, "mcmc_tf.py")).read()
+    cut = src.index("config = tf.ConfigProto(")
+    mod = types.ModuleType("mcmc_tf")
+    mod.__file__ = os.path.join(REF, "mcmc_tf.py")
+    exec(compile(src[:cut], mod.__file__, "exec"), mod.__dict__)
+    return mod
+
+
+ref_mcmc = _load_mcmc_tf()
+
+
+def set_globals(system_shape, K, H, num_samples):
+    """The module constants of mcmc_tf.py:14-32 that its functions read as globals."""
+    g = ref_mcmc
+    g.K, g.H = K, H
+    g.SYSTEM_SHAPE = tuple(system_shape)
+    g.N_DIMS = len(system_shape)
+    g.NUM_SPINS = np.prod(system_shape)
+    g.FULL_WINDOW_SHAPE = (K * 2 - 1,) * g.N_DIMS
+    g.FULL_WINDOW_SIZE = np.prod(g.FULL_WINDOW_SHAPE)
+    g.HALF_WINDOW_SHAPE = (K,) * g.N_DIMS
+    g.HALF_WINDOW_SIZE = np.prod(g.HALF_WINDOW_SHAPE)
+    g.NUM_SAMPLES = num_samples
+
+
+def make_model(spec):
+    """spec = ('CRBM', k, alpha, n_dims) | ('DCRBM', k, layers, n_dims); returns (model, r)."""
+    if spec[0] == "CRBM":
+        _, k, alpha, n_dims = spec
+        return ref_models.CRBM(k, (k - 1) // 2, alpha, n_dims), k
+    _, k, layers, n_dims = spec
+    return ref_models.DCRBM(k, list(layers), n_dims), len(layers) * (k - 1) + 1
+
+
+def param_names(spec):
+    if spec[0] == "CRBM":
+        return ["filters", "bias_vis", "bias_hid"]                  # models.py:19-28
+    return [n % l for l in range(len(spec[2])) for n in ("filters_%d", "bias_%d")]   # models.py:85-92
+
+
+def get_params(spec):
+    with tf.variable_scope("factors", reuse=True):
+        return {n: tf.get_variable(n).numpy() for n in param_names(spec)}
+
+
+def run_case(case, precision):
+    """One pass through the reference in the given precision; returns a dict of arrays."""
+    tf.reset_default_graph()
+    tf.set_precision(precision)
+    tf.set_random_seed(case["seed"])
+    np.random.seed(case["seed"])               # sampler.py:42 names its scope with np.random
+    shape = tuple(case["system_shape"])
+    n_dims = len(shape)
+    ref_models.CRBM.SCALE = ref_models.DCRBM.SCALE = case["scale"]
+    model, r = make_model(case["model"])
+    set_globals(shape, r, case.get("H", 1.0), case["num_samples"])
+    out = {}
+    p0 = get_params(case["model"])
+    for n, v in p0.items():
+        out["param/" + n] = v.astype(np.float32)
+
+    ref_sampler.Sampler.MAX_NUM_SAMPLERS = case.get("max_num_samplers", 1000)
+    smp = ref_sampler.Sampler(model, shape, r, case["num_samples"], case["num_flips"])
+    S = smp.num_samplers
+    out["bookkeeping"] = np.array([smp.num_samplers, smp.its_per_sample, smp.samples_per_sampler,
+                                   smp.therm_its, smp.sample_its, smp.padded_size], np.int64)
+
+    # ---- Sampler.mcmc_op, step by step (sampler.py:158-177 unrolled so that the accept
+    #      decisions can be observed): reset, sample_its x mcmc_step, final reshape
+    nlog0 = len(tf.random_log)
+    smp.mcmc_reset()
+    draws = tf.random_log[nlog0:]
+    assert [k for k, _ in draws] == ["uniform_int", "uniform_int", "uniform_float"]
+    out["initial_states"] = (draws[0][1] * 2 - 1).astype(np.int8)      # sampler.py:74-75
+    out["flip_positions"] = draws[1][1].astype(np.int16 if np.prod(shape) < 32768 else np.int32)
+    out["accept_sample"] = draws[2][1].astype(np.float32)
+    out["reset_factors"] = smp.current_factors_var.numpy()
+    accept = np.zeros((smp.sample_its, S), np.uint8)
+    logratio = np.zeros((smp.sample_its, S), np.float64)
+    i = tf.constant(0)
+    prev_spins = smp.current_samples_var.numpy()
+    prev_fac = smp.current_factors_var.numpy()
+    while bool(i < smp.sample_its):
+        it = int(i)
+        i = smp.mcmc_step(i)
+        spins = smp.current_samples_var.numpy()
+        fac = smp.current_factors_var.numpy()
+        fp = out["flip_positions"][it].astype(np.int64)
+        identity = (fp[:, 0] == fp[:, 1]) if case["num_flips"] == 2 else np.zeros(S, bool)
+        changed = (spins != prev_spins).any(1)
+        # identity proposals (same site twice) are always accepted (ratio 1 > u); they leave no trace
+        accept[it] = changed | identity
+        logratio[it] = np.where(changed, (fac.astype(np.complex128) - prev_fac).sum(1).real, np.nan)
+        prev_spins, prev_fac = spins, fac
+    samples = tf.reshape(smp.samples_var, [smp.num_samples, smp.num_spins]).numpy()   # sampler.py:176-177
+    out["accept"] = accept
+    out["logratio_re"] = logratio.astype(np.float32)
+    out["samples"] = samples.astype(np.int8)
+    out["final_current_samples"] = smp.current_samples_var.numpy().astype(np.int8)
+    out["final_factors"] = smp.current_factors_var.numpy()
+
+    # ---- the same thing through mcmc_op() itself: must reproduce the unrolled run
+    tf.set_random_seed(case["seed"])
+    for n in param_names(case["model"]):       # burn the initializer draws so the stream lines up
+        tf._rng.standard_normal(p0[n].shape)
+    smp.new_samples.load(True)
+    again = smp.mcmc_op().numpy()
+    assert np.array_equal(again, samples), "mcmc_op() != reset + steps"
+
+    # ---- model.factors on the samples (padded as the callers do), log psi
+    pad = [(r - 1) // 2] * n_dims
+    shaped = tf.reshape(tf.constant(samples.astype(np.int32)), (smp.num_samples,) + shape)
+    padded = ref_helpers.pad(shaped, shape, pad)
+    fac = model.factors(padded).numpy()
+    out["factors"] = fac
+    out["padded_samples_row0"] = padded.numpy()[0].astype(np.int8)
+
+    # ---- local energies (mcmc_tf.py:59-141) on the samples; batched_op (mcmc_tf.py:144-153)
+    states = tf.constant(samples.astype(np.int32))
+    if case["hamiltonian"] == "tfim":
+        energy_fn = lambda s: ref_mcmc.ising_energy(model, s)            # noqa: E731
+    else:
+        energy_fn = lambda s: ref_mcmc.heisenberg_energy(model, s)       # noqa: E731
+    if n_dims == 2:
+        e = energy_fn(states).numpy()
+        out["energies"] = e
+        bs = case["num_samples"] // 2
+        eb = ref_mcmc.batched_op(energy_fn, states, bs).numpy()
+        assert np.allclose(eb, e, rtol=1e-5 if precision == "single" else 1e-12)
+        out["loss"] = np.asarray(ref_mcmc.loss_op(tf.constant(fac), tf.constant(e)).numpy())
+
+        # ---- optimize_op twice (mcmc_tf.py:156-179): sample -> energies -> loss -> Adam.
+        #      persistent chains on the second call (sampler.new_samples = it == 0, :219-221)
+        for it in range(2):
+            smp.new_samples.load(it == 0)
+            n0 = len(tf.random_log)
+            energies, _ = ref_mcmc.optimize_op(smp, model, energy_fn)
+            d = tf.random_log[n0:]
+            out["opt%d/initial_states" % it] = (d[0][1] * 2 - 1).astype(np.int8)   # drawn even if unused
+            out["opt%d/flip_positions" % it] = d[1][1].astype(out["flip_positions"].dtype)
+            out["opt%d/accept_sample" % it] = d[2][1]
+            out["opt%d/samples" % it] = tf.reshape(smp.samples_var, [smp.num_samples, smp.num_spins]) \
+                .numpy().astype(np.int8)
+            out["opt%d/energies" % it] = energies.numpy()
+            for n in param_names(case["model"]):
+                out["opt%d/grad/%s" % (it, n)] = tf.train.last_gradients["factors/" + n].numpy()
+            for n, v in get_params(case["model"]).items():
+                out["opt%d/param/%s" % (it, n)] = v
+    return out
+
+
+def helper_vectors():
+    """helpers.py on small deterministic inputs, 1-D / 2-D / 3-D."""
+    tf.reset_default_graph()
+    tf.set_precision("double")
+    out = {}
+    rng = np.random.Generator(np.random.Philox(99))
+    for tag, shape, win in (("1d", (7,), (3,)), ("2d", (4, 5), (3, 3)), ("2d_even", (6, 6), (4, 4)),
+                            ("3d", (3, 4, 3), (3, 3, 3)), ("2d_wrap", (3, 3), (5, 5))):
+        n = int(np.prod(shape))
+        x = rng.integers(-9, 10, size=(3, n)).astype(np.int32)
+        out[tag + "/x"] = x
+        out[tag + "/index_matrix"] = ref_helpers.create_index_matrix(shape, win)
+        out[tag + "/all_windows"] = ref_helpers.all_windows(tf.constant(x), shape, win).numpy()
+        s = (rng.integers(0, 2, size=(3, n)) * 2 - 1).astype(np.int32)
+        out[tag + "/s"] = s
+        out[tag + "/interactions"] = ref_helpers.interactions(tf.constant(s), shape).numpy()
+        p = tuple(min(2, d) for d in shape)
+        xs = x.reshape((3,) + shape)
+        padded = ref_helpers.pad(tf.constant(xs), shape, p)
+        out[tag + "/pad_size"] = np.array(p)
+        out[tag + "/padded"] = padded.numpy()
+        out[tag + "/unpadded"] = ref_helpers.unpad(padded, p).numpy()
+        centers = rng.integers(0, n, size=3).astype(np.int32)
+        out[tag + "/centers"] = centers
+        out[tag + "/gather_windows"] = ref_helpers.gather_windows(tf.constant(x), tf.constant(centers), shape, win).numpy()
+        if any(w > d for w, d in zip(win, shape)):
+            continue                     # window aliases itself: scatter order is undefined
+        var = tf.Variable(x.copy(), trainable=False)
+        upd = rng.integers(100, 200, size=(3,) + win).astype(np.int32)
+        mask = np.array([True, False, True])
+        ref_helpers.update_windows(var, tf.constant(centers), tf.constant(upd.reshape(3, -1)), tf.constant(mask), shape, win)
+        out[tag + "/updates"] = upd
+        out[tag + "/mask"] = mask
+        out[tag + "/update_windows"] = var.numpy()
+    return out
+
+
+def factor_vectors():
+    """model.factors in 1-D, 2-D and 3-D (models.py:56-61, 118-123), float64."""
+    out = {}
+    rng = np.random.Generator(np.random.Philox(7))
+    cases = [("crbm1d", ("CRBM", 3, 2, 1), (8,)), ("crbm2d", ("CRBM", 5, 4, 2), (6, 6)),
+             ("crbm3d", ("CRBM", 3, 2, 3), (4, 4, 4)), ("dcrbm1d", ("DCRBM", 3, (4, 4, 2), 1), (9,)),
+             ("dcrbm2d", ("DCRBM", 3, (4, 4, 2), 2), (8, 8)), ("dcrbm3d", ("DCRBM", 3, (4, 2), 3), (5, 5, 5))]
+    for tag, spec, shape in cases:
+        tf.reset_default_graph()
+        tf.set_precision("double")
+        tf.set_random_seed(11)
+        ref_models.CRBM.SCALE = ref_models.DCRBM.SCALE = 0.3
+        model, r = make_model(spec)
+        s = (rng.integers(0, 2, size=(4,) + shape) * 2 - 1).astype(np.int32)
+        padded = ref_helpers.pad(tf.constant(s), shape, [(r - 1) // 2] * len(shape))
+        out[tag + "/spins"] = s.astype(np.int8)
+        out[tag + "/factors"] = model.factors(padded).numpy()
+        for n, v in get_params(spec).items():
+            out[tag + "/param/" + n] = v.astype(np.float32)
+    return out
+
+
+CASES = {
+    # name: C1 of BASELINE.json (6x6 TFIM, CRBM(5,2,4,2)), sigma 0.1 so that acceptance is non-trivial
+    "c1_tfim_crbm": dict(model=("CRBM", 5, 4, 2), system_shape=(6, 6), hamiltonian="tfim", H=1.0,
+                         num_samples=16, num_flips=1, scale=0.1, seed=2001),
+    # the shipped script's Hamiltonian and sampler (mcmc_tf.py:202-209): Heisenberg, two independent flips
+    "heis_crbm": dict(model=("CRBM", 5, 4, 2), system_shape=(6, 6), hamiltonian="heisenberg",
+                      num_samples=16, num_flips=2, scale=0.1, seed=2002),
+    # deep model, r = 7, on 8x8 with H = 3 (C2-like)
+    "tfim_dcrbm": dict(model=("DCRBM", 3, (4, 4, 2), 2), system_shape=(8, 8), hamiltonian="tfim", H=3.0,
+                       num_samples=8, num_flips=1, scale=0.3, seed=2003),
+    # more samples than samplers: samples_per_sampler = 2, sample row order j * S + chain
+    "tfim_crbm_sps2": dict(model=("CRBM", 5, 4, 2), system_shape=(6, 6), hamiltonian="tfim", H=1.0,
+                           num_samples=8, num_flips=1, scale=0.1, seed=2004, max_num_samplers=4),
+    # deep model under the Heisenberg estimator / pair flips (window K+2, mcmc_tf.py:105-108)
+    "heis_dcrbm": dict(model=("DCRBM", 3, (4, 2), 2), system_shape=(6, 6), hamiltonian="heisenberg",
+                       num_samples=8, num_flips=2, scale=0.3, seed=2005),
+}
+
+
+def main():
+    for name, case in CASES.items():
+        case = dict(case)
+        for attempt in range(20):
+            single = run_case(case, "single")
+            double = run_case(case, "double")
+            if np.array_equal(single["accept"], double["accept"]) and all(
+                    np.array_equal(single[k], double[k]) for k in single if k.endswith("samples")):
+                break
+            case["seed"] += 1000          # a float32 near-tie: take another stream
+        else:
+            raise SystemExit("no tie-free seed for " + name)
+        out = {"seed": np.array(case["seed"])}
+        for k, v in double.items():
+            out[k] = v
+        for k, v in single.items():       # the float32 run: outputs only (inputs are identical)
+            if k.split("/")[0] in ("reset_factors", "final_factors", "factors", "energies", "loss") \
+                    or "/energies" in k or "/grad/" in k or ("/param/" in k and k.startswith("opt")):
+                out["f32/" + k] = v
+        acc = out["accept"].mean()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print("%-16s seed %d  steps %d x %d chains  acceptance %.3f  E/spin %.5f  -> %d kB" % (
+            name, case["seed"], out["accept"].shape[0], out["accept"].shape[1], acc,
+            float(np.real(out["energies"]).mean()),
+            os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024))
+    np.savez_compressed(os.path.join(HERE, "helpers.npz"), **helper_vectors())
+    np.savez_compressed(os.path.join(HERE, "factors_nd.npz"), **factor_vectors())
+    print("helpers.npz, factors_nd.npz written")
+
+
+if __name__ == "__main__":
+    main()
