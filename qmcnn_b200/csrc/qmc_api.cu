@@ -101,6 +101,12 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     h->max_warps_override = mw ? std::atoi(mw) : 0;
     const char* sp = std::getenv("QMC_SWEEP_PATH");
     h->batched_sweep = h->allow_batched && sp && std::strcmp(sp, "batched") == 0;
+    h->allow_ip = !(sp && std::strcmp(sp, "pingpong") == 0);
+    h->force_ip = sp && std::strcmp(sp, "inplace") == 0;
+    const char* is = std::getenv("QMC_IP_SYNC");
+    if (is) h->ip_sync = std::atoi(is);
+    const char* ig = std::getenv("QMC_IP_GROUP");
+    if (ig) h->ip_group = std::atoi(ig);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
@@ -148,6 +154,11 @@ size_t qmc_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips) {
     if (slots < 0) return 0;
     size_t f = (size_t)slots * pl.staging_floats;
     if (num_flips == 1) {
+        const IpLaunch il = ip_launch_plan(h, S);
+        if (il.ok) {
+            const size_t b = (size_t)il.grid * il.warps * il.ip.staging_floats;
+            if (b > f) f = b;
+        }
         const LeanLaunch ll = lean_launch_plan(h, S);
         if (ll.ok) {
             const size_t b = (size_t)ll.grid * ll.warps * ll.staging_floats;
@@ -246,8 +257,11 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
                     n_sample_slots, accept_trace, logratio_trace, n_accept};
         cudaError_t e;
         LeanLaunch ll{};
+        IpLaunch il{};
         if (num_flips == 1 && h->batched_sweep && batched_supported(h))
             e = launch_sweep_batched(h, a, (cudaStream_t)stream, h->err);
+        else if (num_flips == 1 && !h->allow_lean && (il = ip_launch_plan(h, S)).ok)
+            e = launch_sweep_ip(h, a, il, (cudaStream_t)stream);
         else if (num_flips == 1 && (ll = lean_launch_plan(h, S)).ok)
             e = launch_sweep_lean(h, a, ll, (cudaStream_t)stream);
         else

@@ -19,6 +19,11 @@ struct qmc_handle {
     bool allow_tiled = true;  // QMC_FORCE_GENERIC=1 disables the specialised conv instances
     int max_warps_override = 0;  // QMC_MAX_WARPS: tuning knob, caps the warps per CTA of the persistent kernels
     bool allow_lean = false;     // QMC_LEAN=1: lean persistent sweep kernel (more warps, smaller tiles); off by default
+    bool allow_ip = true;        // QMC_SWEEP_PATH=pingpong disables the in-place persistent sweep kernel (k_sweep_ip)
+    int ip_group = 4;            // QMC_IP_GROUP: warps per phase group of k_sweep_ip<3>
+    int ip_sync = 3;             // QMC_IP_SYNC: barriers of k_sweep_ip (0 none, 1 CTA per proposal, 2 CTA per layer,
+                                 // 3 = per layer within a phase group of ip_group warps - the default, fastest)
+    bool force_ip = false;       // QMC_SWEEP_PATH=inplace: use k_sweep_ip whenever the model is inside its coverage
     bool allow_batched = true;  // QMC_FORCE_PERSISTENT=1 disables the layer-synchronous batched path (energy + sweep)
     bool batched_sweep = false; // QMC_SWEEP_PATH=batched: use the batched path for the sweep too (default: persistent
                                 // kernel, which is faster at a few thousand chains per GPU - DESIGN.md)
@@ -164,6 +169,10 @@ cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t s
 struct LeanLaunch { LeanPlan lp; int warps, grid; size_t smem; int newf_floats, spins_bytes, staging_floats; bool ok; };
 LeanLaunch lean_launch_plan(const qmc_handle* h, int S);
 cudaError_t launch_sweep_lean(const qmc_handle* h, const SweepArgs& a, const LeanLaunch& ll, cudaStream_t st);
+struct IpLaunch { IpPlan ip; int warps, grid; size_t smem; bool ok; };
+IpPlan ip_plan(const qmc_handle* h);
+IpLaunch ip_launch_plan(const qmc_handle* h, int S);
+cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st);
 cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, double* drel, cudaStream_t st,
                              std::string& err);
 int sweep_sym_slots(const qmc_handle* h, int S, int num_flips, int nsym, EvalPlan* plan, WarpGrid* grid);

@@ -1,0 +1,279 @@
+// qmc_sweep_ip.cu - the persistent Metropolis kernel with the in-place evaluator.
+// Same per-proposal protocol as k_sweep (qmc_sweep.cu; sampler.py:104-155) and bit-identical
+// results; the difference is warp_eval_flip_ip: one tile arena per warp instead of two ping-pong
+// tiles, so that ~12 instead of 7 chains are resident per SM at C3 (3 warps per scheduler
+// instead of 1.75 - the classic kernel issues on only 44% of cycles because each scheduler has
+// fewer than two warps to choose from).  Single-flip proposals of deep k = 3 models whose
+// windows fit one round of the register tile; everything else runs the classic kernel.
+#include "qmc_host.h"
+#include "qmc_ip.cuh"
+
+namespace qmc {
+
+constexpr int kIpMaxWarps = 12;       // 384 threads -> 168 registers per thread
+constexpr int kIpAcc = 64;            // accumulators per lane
+
+// Time slicing (host side, launch_sweep_ip): the S x n_steps proposals are cut into tasks
+// (chunk of `chunk_len` consecutive steps, chain), numbered chunk-major, and every launch hands
+// ONE task to every warp slot.  A chain's chunks are in different launches (S >= slots), so the
+// stream orders them; every launch is exactly one full wave, so there is no idle tail whatever S
+// is (4096 chains on 148 x 12 slots would otherwise be 2.3 waves = 77% efficiency).
+struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps; };
+
+// SYNC: 0 = warps run free; 1 = one CTA barrier per proposal; 2 = one per layer as well; 3 = per
+// layer among the four warps of a phase group (ip_barrier).  With barriers the warps of a group
+// stay in the same phase of the proposal, so the SM's instruction working set is a few loop
+// bodies instead of twelve (the free-running version is instruction-fetch bound: 93% of the
+// GPC instruction-cache request rate, profiles/r01_summary.md).  Warps without a task or past
+// their chunk's end shadow a valid chain without writing anything, to keep barrier counts equal.
+template <int SYNC>
+__global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
+k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip, IpSlice sl) {
+    extern __shared__ float4 smem4[];
+    float* smem_f = reinterpret_cast<float*>(smem4);
+    load_params_to_smem(m, params, smem_f);
+    const float* sp = smem_f;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // division magics W_j = 2(j+2)p + 1 in shared memory: indexing the kernel-parameter array by layer would
+    // make ptxas keep a local-memory copy, and those loads miss L1 (28 KB next to 220 KB of shared memory)
+    unsigned* mg = reinterpret_cast<unsigned*>(smem_f + m.smem_param_floats);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < QMC_MAX_LAYERS; ++j) mg[j] = ip.mgW[j];
+    }
+    __syncthreads();
+    char* wmem = reinterpret_cast<char*>(mg + QMC_MAX_LAYERS) + (size_t)warp * ip.per_warp_bytes;
+    float* arena = reinterpret_cast<float*>(wmem);
+    float* spt = arena + ip.arena_floats;
+    int8_t* spins_s = reinterpret_cast<int8_t*>(spt + ip.spt_floats);
+
+    const int n = m.n, p = m.p, Ly = m.Ly, Lx = m.Lx, D = m.D;
+    const int slot = blockIdx.x * nwarps + warp;
+    float* staging = a.staging + (size_t)slot * ip.staging_floats;
+    const float* newf = arena + ip.newf_off;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const int lside = 1 + 2 * D * p;                       // window of the last layer
+    unsigned long long accepted = 0;
+    // phase group of this warp (SYNC == 3): warps 4g .. 4g+3, named barrier 1 + g
+    const int gw = sl.group_warps, g = warp / gw;
+    const int gid = 1 + g;
+    const int gthreads = 32 * min(gw, nwarps - g * gw);
+
+    const long long task = sl.task0 + slot;
+    const bool has_task = task < sl.n_tasks;
+    if (!SYNC && !has_task) return;
+    const long long tt = has_task ? task : sl.n_tasks - 1;
+    const long long chunk = tt / a.S;
+    const int chain = (int)(tt - chunk * a.S);
+    const long long it0 = chunk * sl.chunk_len;
+    const long long it1 = min(it0 + sl.chunk_len, a.n_steps);
+    {
+        int8_t* gspins = a.spins + (size_t)chain * n;
+        float* cache = a.cache + (size_t)chain * m.cache_floats;
+        for (int i = lane; i < n; i += kWarp) spins_s[i] = gspins[i];
+        __syncwarp();
+        const unsigned long long gchain = (unsigned long long)(a.chain_id0 + chain);
+        // (flip site, uniform) of iteration `it`: Philox-4x32-10 keyed by (seed; step, global chain), or fed in
+        auto draw = [&](long long it, int& f, float& uu) {
+            if (a.flip_pos) {
+                f = a.flip_pos[(size_t)it * a.S + chain];
+                uu = a.uniforms[(size_t)it * a.S + chain];
+            } else {
+                const long long step = a.step0 + it;
+                const uint4 r = philox4x32_10(
+                    make_uint4((uint32_t)step, (uint32_t)((unsigned long long)step >> 32),
+                               (uint32_t)gchain, (uint32_t)(gchain >> 32)), key);
+                f = (int)__umulhi(r.x, (uint32_t)n);
+                uu = (float)(r.w >> 8) * 5.9604644775390625e-8f;   // 2^-24
+            }
+            f = __shfl_sync(0xffffffffu, f, 0);
+            uu = __shfl_sync(0xffffffffu, uu, 0);
+        };
+        int f_next = 0;
+        float u_next = 0.f;
+        draw(it0 < it1 ? it0 : it1 - 1, f_next, u_next);
+        for (long long itx = it0; itx < it0 + sl.chunk_len; ++itx) {
+            const bool active = has_task && itx < it1;
+            if (!SYNC && !active) break;
+            const long long it = active ? itx : it1 - 1;      // shadow steps re-evaluate the last one
+            const long long step = a.step0 + it;
+            const int f0 = f_next;
+            const float u = u_next;
+            if (itx + 1 < it1) draw(itx + 1, f_next, u_next);   // one step ahead: the loads / Philox rounds overlap the evaluation
+            float dre;
+            ip_barrier<SYNC>(gid, gthreads);
+            warp_eval_flip_ip<kIpAcc, SYNC>(m, ip, sp, mg, arena, spt, spins_s, cache, staging, f0, lane, gid, gthreads, dre);
+            const float amp = expf(dre);                      // |exp(z)| = exp(Re z)
+            const bool accept = __shfl_sync(0xffffffffu, (int)(amp * amp > u), 0) != 0;   // strict, sampler.py:125
+            if (SYNC && !active) continue;                    // shadow: nothing is written
+            if (accept) {
+                // commit: new hidden activations (from staging), new factors, the spin
+                const int y0 = f0 / Lx, x0 = f0 - y0 * Lx;
+                int stg = 0, side = 1;
+                for (int l = 0; l < D - 1; ++l) {
+                    const LayerInfo& L = m.layer[l];
+                    side += 2 * p;
+                    const int rarea = side * side, ncg = L.coutp >> 2;
+                    const int ry = y0 - (l + 1) * p, rx = x0 - (l + 1) * p;
+                    float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
+                    const FastDiv dside(l ? mg[l - 1] : ip.mg2p1, side);   // side = W_{l-1}, or 2p + 1
+                    for (int base = 0; base < rarea; base += 2 * kWarp) {
+                        // two sites per lane and pass, all channel groups of a site by the same lane:
+                        // one index computation per site instead of one per float4
+                        int pos[2], site[2];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            pos[j] = base + j * kWarp + lane;
+                            site[j] = -1;
+                            if (pos[j] < rarea) {
+                                const int y = dside.div(pos[j]), x = pos[j] - y * side;
+                                site[j] = wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx);
+                            }
+                        }
+                        for (int cg0 = 0; cg0 < ncg; cg0 += 2) {
+                            float4 v[2][2];       // (four channel groups in flight spill at 168 registers: measured slower)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    if (site[j] >= 0 && cg0 + q < ncg)
+                                        v[j][q] = ldcg4(staging + stg + (size_t)((cg0 + q) * rarea + pos[j]) * 4);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    if (site[j] >= 0 && cg0 + q < ncg)
+                                        plane4[(cg0 + q) * n + site[j]] = v[j][q];
+                        }
+                    }
+                    stg += L.coutp * rarea;
+                }
+                const int ry = y0 - D * p, rx = x0 - D * p;
+                const FastDiv dls(mg[D - 2], lside);
+                for (int pos = lane; pos < lside * lside; pos += kWarp) {
+                    const int y = dls.div(pos), x = pos - y * lside;
+                    cache[m.fre_off + wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx)] = newf[pos];
+                }
+                if (lane == 0) spins_s[f0] = -spins_s[f0];
+                __syncwarp();
+                ++accepted;
+            }
+            if (lane == 0) {
+                if (a.accept_trace) a.accept_trace[(size_t)it * a.S + chain] = accept ? 1 : 0;
+                if (a.logratio_trace) a.logratio_trace[(size_t)it * a.S + chain] = dre;
+            }
+            // sample write-out AFTER the update (sampler.py:135-152)
+            if (a.samples && step >= a.therm_its && (step - a.therm_its) % a.its_per_sample == 0) {
+                const long long j = (step - a.therm_its) / a.its_per_sample;
+                if (j < a.n_sample_slots) {
+                    int8_t* dst = a.samples + ((size_t)j * a.S + chain) * n;
+                    for (int i = lane; i < n; i += kWarp) dst[i] = spins_s[i];
+                }
+            }
+        }
+        if (has_task)
+            for (int i = lane; i < n; i += kWarp) gspins[i] = spins_s[i];
+        __syncwarp();
+    }
+    if (a.n_accept && lane == 0 && accepted) atomicAdd(a.n_accept, accepted);
+}
+
+// Is the model inside the in-place evaluator's coverage, and what does a warp need?
+IpPlan ip_plan(const qmc_handle* h) {
+    IpPlan ip{};
+    const DevModel& m = h->m;
+    if (!h->allow_tiled || m.kind != QMC_MODEL_DCRBM || m.D < 2 || m.k != 3) return ip;
+    if (1 + 2 * m.D * m.p > m.Ly || 1 + 2 * m.D * m.p > m.Lx) return ip;      // box_supported(1, 1)
+    const int p = m.p;
+    int cmax = 0, staging = 0;
+    for (int l = 0; l < m.D; ++l) {
+        const LayerInfo& L = m.layer[l];
+        const int side = 1 + 2 * (l + 1) * p, npos = side * side;
+        if (l >= 1) {
+            const bool hidden_ok = (L.cin == 16 && L.cout == 16) || (L.cin == 8 && L.cout == 8);
+            const bool last_ok = hidden_ok || (L.cin == 16 && L.cout == 8);
+            if (l < m.D - 1 ? !hidden_ok : !last_ok) return ip;
+            const int P = ip_sites_per_lane(kIpAcc, L.cout, npos);
+            if ((npos + P - 1) / P > kWarp) return ip;                        // must be ONE round
+        }
+        if (l < m.D - 1) {
+            if (L.coutp > cmax) cmax = L.coutp;
+            staging += L.coutp * npos;
+        }
+    }
+    if ((1 + 2 * m.D * p) * (1 + 2 * m.D * p) > 8 * kWarp) return ip;      // head: at most 8 sites per lane
+    ip.T = 1 + 2 * (m.D + 1) * p;
+    ip.tarea = ip.T * ip.T;
+    ip.c = (m.D + 1) * p;
+    const int lside = 1 + 2 * m.D * p, theta = m.layer[m.D - 1].coutp * lside * lside;
+    ip.newf_off = round4(theta);
+    int arena = ip.tarea * cmax;
+    if (ip.newf_off + round4(lside * lside) > arena) arena = ip.newf_off + round4(lside * lside);
+    ip.arena_floats = round4(arena);
+    ip.spt_floats = round4((1 + 4 * p) * (1 + 4 * p));
+    ip.staging_floats = round4(staging);
+    ip.spins_bytes = (m.n + 15) & ~15;
+    ip.per_warp_bytes = (ip.arena_floats + ip.spt_floats) * 4 + ip.spins_bytes;
+    ip.mg2p = fastdiv_magic(2 * p);
+    ip.mg2p1 = fastdiv_magic(2 * p + 1);
+    for (int j = 0; j < m.D; ++j) ip.mgW[j] = fastdiv_magic(2 * (j + 2) * p + 1);
+    ip.ok = 1;
+    return ip;
+}
+
+IpLaunch ip_launch_plan(const qmc_handle* h, int S) {
+    IpLaunch L{};
+    L.ok = false;
+    if (!h->allow_ip) return L;
+    L.ip = ip_plan(h);
+    if (!L.ip.ok) return L;
+    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + QMC_MAX_LAYERS * sizeof(unsigned);
+    if (h->max_smem < cta_bytes + (size_t)L.ip.per_warp_bytes) return L;
+    int w = (int)((h->max_smem - cta_bytes) / (size_t)L.ip.per_warp_bytes);
+    if (w > kIpMaxWarps) w = kIpMaxWarps;
+    if (h->max_warps_override > 0 && w > h->max_warps_override) w = h->max_warps_override;
+    // the classic kernel keeps bigger register tiles; in-place only pays when it adds warps
+    EvalPlan pl = eval_plan(h->m, 1, 1, false);
+    const WarpGrid gc = pick_warp_grid(h, pl.per_warp_bytes, 0, S);
+    if (!h->force_ip && gc.ok && (gc.warps > 8 || w <= gc.warps)) return L;
+    // fewer chains than slots: one launch, as few warps per CTA as cover S (more shared memory per warp is no use)
+    const long long ctas = h->num_sms;
+    if ((long long)S < ctas * w) w = (int)((S + ctas - 1) / ctas);
+    L.warps = w;
+    const long long need = ((long long)S + w - 1) / w;
+    L.grid = (int)(need < ctas ? need : ctas);
+    L.smem = cta_bytes + (size_t)L.ip.per_warp_bytes * w;
+    L.ok = true;
+    return L;
+}
+
+cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st) {
+    const int sy = h->ip_sync;
+    auto kern = sy == 3 ? k_sweep_ip<3> : sy == 2 ? k_sweep_ip<2> : sy == 1 ? k_sweep_ip<1> : k_sweep_ip<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return e;
+    const long long slots = (long long)L.grid * L.warps;
+    // time slicing: chunks of >= 64 steps, at most 64 chunks per chain; one chunk when S fits the slots
+    long long chunks = 1;
+    if ((long long)a.S > slots) {
+        chunks = a.n_steps / 64;
+        if (chunks > 64) chunks = 64;
+        if (chunks < 1) chunks = 1;
+    }
+    IpSlice sl;
+    sl.group_warps = h->ip_group > 0 ? h->ip_group : 4;
+    sl.chunk_len = (a.n_steps + chunks - 1) / chunks;
+    chunks = (a.n_steps + sl.chunk_len - 1) / sl.chunk_len;
+    sl.n_tasks = chunks * a.S;
+    for (sl.task0 = 0; sl.task0 < sl.n_tasks; sl.task0 += slots) {
+        const long long left = sl.n_tasks - sl.task0;
+        const long long ctas = ((left < slots ? left : slots) + L.warps - 1) / L.warps;
+        ++g_launches;
+        kern<<<(int)ctas, L.warps * 32, L.smem, st>>>(h->m, h->d_params, a, L.ip, sl);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+} // namespace qmc

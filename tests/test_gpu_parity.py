@@ -446,3 +446,36 @@ def test_full_size_c3_properties():
     d = (lp_after - lp_before).real[acc].cpu().numpy()
     assert acc.any()
     assert np.abs(d - smp.logratio_trace[0][acc].cpu().numpy()).max() < 2e-3   # difference of two ~1e3 totals in fp32
+
+
+@pytest.mark.parametrize("layers,shape,S", [([16, 16, 16, 16, 16, 8], (20, 20), 40), ([8, 8, 8], (10, 10), 50),
+                                            ([16, 16, 8], (9, 8), 17), ([16, 8], (7, 9), 9), ([8, 8], (5, 6), 33)])
+def test_inplace_kernel_is_bit_identical_to_classic(layers, shape, S):
+    """k_sweep_ip (one in-place tile arena per warp, 12 warps per SM) against the classic ping-pong kernel:
+    decisions, log-ratios, states, samples and the incrementally maintained caches, bit for bit."""
+    from gpu_util import make_pair
+    q = _q()
+    r = len(layers) * 2 + 1
+    outs = []
+    for path in ("pingpong", "inplace"):
+        os.environ["QMC_SWEEP_PATH"] = path
+        try:
+            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 23, layers=layers)
+            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+            init = (np.random.default_rng(4).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+            smp = GS(gm, shape, r, 2 * S, 1, seed=7, chain_id0=11)
+            smp.feed(initial_states=init)
+            samples = smp.mcmc_op(trace=True)
+            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
+                         smp.current_factors_var.clone(), smp._cache.clone()))
+        finally:
+            os.environ.pop("QMC_SWEEP_PATH", None)
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert 0 < int(a[0].sum()) < a[0].numel()
+    h = gm.handle(shape)
+    cf, n = h.cache_floats, shape[0] * shape[1]
+    ca, cb = a[5].view(S, cf), b[5].view(S, cf)
+    used = cf - 2 * ((n + 3) // 4 * 4) + n          # everything up to and including fRe
+    assert torch.equal(ca[:, :used], cb[:, :used])
