@@ -93,6 +93,19 @@ __device__ __forceinline__ void ip_barrier(int gid, int gthreads) {
 // SYNC == 2: a CTA barrier in front of every layer, so that all warps of the SM run the same loop
 // body at the same time (instruction-cache locality; every warp of the CTA must call this the same
 // number of times).
+// commit: scatter the staged window of layer l (src: [cog][pos] float4, in shared memory) into the cache plane
+__device__ __forceinline__ void ip_scatter_layer(const DevModel& m, const LayerInfo& L, const float4* src, float* cache,
+                                                 int side, unsigned mg_side, int ry, int rx, int lane) {
+    const int rarea = side * side, ncg = L.coutp >> 2, n = m.n;
+    float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
+    const FastDiv dside(mg_side, side);
+    for (int pos = lane; pos < rarea; pos += kWarp) {
+        const int y = dside.div(pos), x = pos - y * side;
+        const int site = wrap1(ry + y, m.Ly) * m.Lx + wrap1(rx + x, m.Lx);
+        for (int cg = 0; cg < ncg; ++cg) plane4[cg * n + site] = src[cg * rarea + pos];
+    }
+}
+
 template <int ACC, int SYNC>
 __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPlan& ip, const float* sp,
                                                   const unsigned* mg, float* arena, float* spt, const int8_t* spins_s,
@@ -179,6 +192,10 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         __syncwarp();
     }
     if (SYNC >= 2) ip_barrier<SYNC>(gid, gthreads);
+    // commit, part 1 (speculative): the staged windows of the first layers start their way from L2 into the
+    // free part of the arena now, so that an accepted move finds them in shared memory after the head
+    for (int i = lane * 4; i < ip.spec_floats; i += kWarp * 4) cp_async16(arena + ip.spec_off + i, staging + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // head over the last window: same lane ownership and order as warp_eval_flip
     const int npos = side * side, ry = y0 - D * p, rx = x0 - D * p;
     float* newf = arena + ip.newf_off;

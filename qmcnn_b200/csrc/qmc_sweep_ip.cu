@@ -102,52 +102,49 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
             const float u = u_next;
             if (itx + 1 < it1) draw(itx + 1, f_next, u_next);   // one step ahead: the loads / Philox rounds overlap the evaluation
             float dre;
+            cp_async_wait_all();                              // (a rejected move's speculative commit copy)
             ip_barrier<SYNC>(gid, gthreads);
             warp_eval_flip_ip<kIpAcc, SYNC>(m, ip, sp, mg, arena, spt, spins_s, cache, staging, f0, lane, gid, gthreads, dre);
             const float amp = expf(dre);                      // |exp(z)| = exp(Re z)
             const bool accept = __shfl_sync(0xffffffffu, (int)(amp * amp > u), 0) != 0;   // strict, sampler.py:125
             if (SYNC && !active) continue;                    // shadow: nothing is written
             if (accept) {
-                // commit: new hidden activations (from staging), new factors, the spin
+                // commit: new hidden activations, new factors, the spin.  The staged windows travel L2 -> shared
+                // memory in bulk (linear cp.async: the first layers went ahead during the head, the rest follow in
+                // as few batches as fit the arena below the new factors) and are scattered from there, instead of
+                // one L2 round trip per 2 sites x 2 channel groups (that loop was 10% of the kernel's time).
                 const int y0 = f0 / Lx, x0 = f0 - y0 * Lx;
-                int stg = 0, side = 1;
-                for (int l = 0; l < D - 1; ++l) {
+                cp_async_wait_all();
+                __syncwarp();
+                int stg = 0, side = 1, l = 0;
+                for (; l < ip.spec_layers; ++l) {
                     const LayerInfo& L = m.layer[l];
                     side += 2 * p;
-                    const int rarea = side * side, ncg = L.coutp >> 2;
-                    const int ry = y0 - (l + 1) * p, rx = x0 - (l + 1) * p;
-                    float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
-                    const FastDiv dside(l ? mg[l - 1] : ip.mg2p1, side);   // side = W_{l-1}, or 2p + 1
-                    for (int base = 0; base < rarea; base += 2 * kWarp) {
-                        // two sites per lane and pass, all channel groups of a site by the same lane:
-                        // one index computation per site instead of one per float4
-                        int pos[2], site[2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            pos[j] = base + j * kWarp + lane;
-                            site[j] = -1;
-                            if (pos[j] < rarea) {
-                                const int y = dside.div(pos[j]), x = pos[j] - y * side;
-                                site[j] = wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx);
-                            }
-                        }
-                        for (int cg0 = 0; cg0 < ncg; cg0 += 2) {
-                            float4 v[2][2];       // (four channel groups in flight spill at 168 registers: measured slower)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                                for (int q = 0; q < 2; ++q)
-                                    if (site[j] >= 0 && cg0 + q < ncg)
-                                        v[j][q] = ldcg4(staging + stg + (size_t)((cg0 + q) * rarea + pos[j]) * 4);
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                                for (int q = 0; q < 2; ++q)
-                                    if (site[j] >= 0 && cg0 + q < ncg)
-                                        plane4[(cg0 + q) * n + site[j]] = v[j][q];
-                        }
+                    ip_scatter_layer(m, L, reinterpret_cast<const float4*>(arena + ip.spec_off + stg), cache, side,
+                                     l ? mg[l - 1] : ip.mg2p1, y0 - (l + 1) * p, x0 - (l + 1) * p, lane);
+                    stg += L.coutp * side * side;
+                }
+                while (l < D - 1) {
+                    // batch [l, l1): consecutive layers whose staged windows fit below the new factors
+                    int l1 = l, fl = 0, sd = side;
+                    while (l1 < D - 1) {
+                        const int s2 = sd + 2 * p, add = m.layer[l1].coutp * s2 * s2;
+                        if (l1 > l && fl + add > ip.newf_off) break;
+                        fl += add; sd = s2; ++l1;
                     }
-                    stg += L.coutp * rarea;
+                    __syncwarp();                                  // earlier scatter reads of the arena are done
+                    for (int i = lane * 4; i < fl; i += kWarp * 4) cp_async16(arena + i, staging + stg + i);
+                    cp_async_wait_all();
+                    __syncwarp();
+                    int off = 0;
+                    for (; l < l1; ++l) {
+                        const LayerInfo& L = m.layer[l];
+                        side += 2 * p;
+                        ip_scatter_layer(m, L, reinterpret_cast<const float4*>(arena + off), cache, side,
+                                         l ? mg[l - 1] : ip.mg2p1, y0 - (l + 1) * p, x0 - (l + 1) * p, lane);
+                        off += L.coutp * side * side;
+                    }
+                    stg += fl;
                 }
                 const int ry = y0 - D * p, rx = x0 - D * p;
                 const FastDiv dls(mg[D - 2], lside);
@@ -207,10 +204,25 @@ IpPlan ip_plan(const qmc_handle* h) {
     ip.tarea = ip.T * ip.T;
     ip.c = (m.D + 1) * p;
     const int lside = 1 + 2 * m.D * p, theta = m.layer[m.D - 1].coutp * lside * lside;
-    ip.newf_off = round4(theta);
     int arena = ip.tarea * cmax;
-    if (ip.newf_off + round4(lside * lside) > arena) arena = ip.newf_off + round4(lside * lside);
+    const int nf = round4(lside * lside);
+    if (round4(theta) + nf > arena) arena = round4(theta) + nf;
     ip.arena_floats = round4(arena);
+    ip.newf_off = ip.arena_floats - nf;                          // new factors at the end of the arena
+    // a single layer's staged window must fit below them (commit batches), else not covered
+    for (int l = 0; l < m.D - 1; ++l) {
+        const int side = 1 + 2 * (l + 1) * p;
+        if (m.layer[l].coutp * side * side > ip.newf_off) return ip;
+    }
+    ip.spec_off = round4(theta);
+    ip.spec_layers = 0;
+    ip.spec_floats = 0;
+    for (int l = 0; l < m.D - 1; ++l) {
+        const int side = 1 + 2 * (l + 1) * p, add = m.layer[l].coutp * side * side;
+        if (ip.spec_off + ip.spec_floats + add > ip.newf_off) break;
+        ip.spec_floats += add;
+        ++ip.spec_layers;
+    }
     ip.spt_floats = round4((1 + 4 * p) * (1 + 4 * p));
     ip.staging_floats = round4(staging);
     ip.spins_bytes = (m.n + 15) & ~15;
