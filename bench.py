@@ -304,6 +304,13 @@ def run_cuda(args, cfg, name):
     for _ in range(args.warmup):
         step(False)
     sync()
+    # launches of the sweep kernel in one mcmc_op (the reset forward is one more launch)
+    l0 = _lib.load().qmc_launch_count()
+    sampler._sweep(0, its)
+    sweep_launches = int(_lib.load().qmc_launch_count() - l0)
+    # the classic persistent kernel is always ONE launch; more than one means the in-place kernel, time-sliced
+    sweep_kernel = "k_sweep_ip" if sweep_launches > 1 else "k_sweep / k_sweep_ip (single launch: chains <= warp slots)"
+    sync()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
@@ -374,7 +381,10 @@ def run_cuda(args, cfg, name):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        sweep_s = sw_ms * 1e-3 / args.steps                       # one k_sweep launch (+ the reset forward, <1%)
+        # the sweep segment of one step: the reset forward (<1%) + the launches of the sweep kernel.  For deep
+        # models that is k_sweep_ip, time-sliced by the host into full-wave launches (one chunk of one chain per
+        # warp slot); total proposals / total time equals the launch-weighted mean of per-launch rates.
+        sweep_s = sw_ms * 1e-3 / args.steps
         props_per_launch = float(S) * its
         ach_tflops = props_per_launch * work["flop"] / sweep_s * 1e-12
         # which of the three rooflines bounds one proposal:
@@ -385,7 +395,7 @@ def run_cuda(args, cfg, name):
         t_b = work["window_bytes"] * (1 + accept_rate) / (hbm_peak * 1e9)
         bound = "fp32_fma" if t_f >= max(t_m, t_b) else ("mufu" if t_m >= t_b else "hbm")
         roofline = {
-            "kernel": "k_sweep", "bound": bound, "bound_times_ns": {"fp32": t_f * 1e9, "mufu": t_m * 1e9, "hbm": t_b * 1e9},
+            "kernel": sweep_kernel, "bound": bound, "bound_times_ns": {"fp32": t_f * 1e9, "mufu": t_m * 1e9, "hbm": t_b * 1e9},
             "frac_of_bound": max(t_f, t_m, t_b) / (sweep_s / props_per_launch),
             "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": ach_tflops / fp32_peak if fp32_peak else None,
@@ -399,10 +409,12 @@ def run_cuda(args, cfg, name):
             "mufu_gops_peak": mufu.value,
             "traffic": None,
         }
+        roofline["sweep_kernel_launches_per_step"] = sweep_launches
+        roofline["proposals_per_launch"] = props_per_launch / max(sweep_launches, 1)
         prof = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
         if os.path.exists(prof):
             try:
-                roofline["traffic"] = json.load(open(prof))["dram_bytes_per_proposal"] * props_per_launch
+                roofline["traffic"] = json.load(open(prof))["dram_bytes_per_proposal"] * roofline["proposals_per_launch"]
                 roofline["traffic_source"] = "profiles/r01_sweep_traffic.json (ncu dram__bytes per proposal x proposals per launch)"
             except Exception:
                 pass

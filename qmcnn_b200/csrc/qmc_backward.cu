@@ -11,6 +11,8 @@
 // parameter gradient is accumulated per CTA in shared memory and the CTAs'
 // partial vectors are summed in a fixed order by k_backward_reduce, so the
 // result is deterministic for a given launch geometry.
+#include <cstdlib>
+#include <cstring>
 #include "qmc_host.h"
 
 namespace qmc {
@@ -177,6 +179,179 @@ k_backward(DevModel m, const float* __restrict__ params, const int8_t* __restric
     for (int i = threadIdx.x; i < m.P; i += blockDim.x) partial[(size_t)blockIdx.x * m.P + i] = acc[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_backward_smem: the same computation with everything a layer touches staged in shared memory.
+// One CTA per SM walks samples grid-stride; per sample and layer the input activation plane
+// (from the K1 cache), the cotangent plane G and the cotangent below Gn live in shared memory
+// next to the padded parameter block and the CTA's gradient accumulator, so the 9 x C_in x C_out
+// re-reads of every site hit shared memory instead of L2 (the first version ran at <1% of the
+// FP32 roofline).  Planes are channel-group planar float4 [cg][site] like the cache: consecutive
+// threads (consecutive sites) read consecutive 16-byte words.  Every sum keeps the order of
+// k_backward (taps, then channels, then sites ascending), one owner thread per gradient element:
+// deterministic.  Used when the planes fit (lattices up to ~24 x 24 at 16 channels); larger
+// lattices run k_backward.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwdSmemThreads = 576;      // = 9 taps x 16 C_in x 4 channel groups: one weight-gradient round
+
+__global__ void __launch_bounds__(kBwdSmemThreads, 1)
+k_backward_smem(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins,
+                const float2* __restrict__ weights, int N, const float* __restrict__ cache_all,
+                float* __restrict__ partial, int plane_floats) {
+    extern __shared__ float4 smem4[];
+    float* sp = reinterpret_cast<float*>(smem4);
+    float* acc = sp + m.smem_param_floats;                  // P floats, caller's flat order
+    float* A = acc + round_up4(m.P);                        // input plane of the current layer
+    float* G = A + plane_floats;                            // cotangent of the current layer's output
+    float* Gn = G + plane_floats;                           // cotangent of its input
+    load_params_to_smem(m, params, sp);
+    for (int i = threadIdx.x; i < m.P; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const int n = m.n, Ly = m.Ly, Lx = m.Lx, k = m.k, p = m.p, D = m.D;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    for (int s = blockIdx.x; s < N; s += gridDim.x) {
+        const float* cache = cache_all + (size_t)s * m.cache_floats;
+        const int8_t* sx = spins + (size_t)s * n;
+        const float2 w = weights[s];
+        // input plane of the last layer
+        auto stage_input = [&](int l) {
+            if (l == 0) {
+                for (int i = tid; i < n; i += nthr) A[i] = (float)sx[i];
+            } else {
+                const LayerInfo& Lp = m.layer[l - 1];
+                const float4* src = reinterpret_cast<const float4*>(cache + Lp.act_off);
+                float4* dst = reinterpret_cast<float4*>(A);
+                for (int i = tid; i < (Lp.coutp >> 2) * n; i += nthr) dst[i] = __ldcg(src + i);
+            }
+        };
+        stage_input(D - 1);
+        __syncthreads();
+        // ---- head: theta of the last layer, cotangent G_D = (Re, Im)(w conj tanh theta) ----------
+        {
+            const LayerInfo& L = m.layer[D - 1];
+            const int half = L.cout >> 1;
+            for (int i = tid; i < (L.coutp >> 2) * n * 4; i += nthr) G[i] = 0.f;      // padded channels stay zero
+            __syncthreads();
+            for (int t = tid; t < n * half; t += nthr) {
+                const int c = t / n, site = t - c * n;            // consecutive threads: consecutive sites
+                const int y = site / Lx, x = site - y * Lx;
+                float th[2];
+                for (int part = 0; part < 2; ++part) {
+                    const int co = c + part * half;
+                    float a = sp[L.sb_off + co];
+                    for (int dy = 0; dy < k; ++dy) {
+                        const int qy = wrap1(y + dy - p, Ly) * Lx;
+                        for (int dx = 0; dx < k; ++dx) {
+                            const int q = qy + wrap1(x + dx - p, Lx);
+                            const float* wr = sp + L.sw_off + (dy * k + dx) * L.cin * L.coutp + co;
+                            if (D == 1) {
+                                a = fmaf(A[q], wr[0], a);
+                            } else {
+                                for (int ci = 0; ci < L.cin; ++ci)
+                                    a = fmaf(A[((ci >> 2) * n + q) * 4 + (ci & 3)], wr[ci * L.coutp], a);
+                            }
+                        }
+                    }
+                    th[part] = a;
+                }
+                const float2 tc = ctanh_stable(th[0], th[1]);
+                const int c2 = c + half;
+                G[((c >> 2) * n + site) * 4 + (c & 3)] = w.x * tc.x + w.y * tc.y;       // w * conj(t)
+                G[((c2 >> 2) * n + site) * 4 + (c2 & 3)] = w.y * tc.x - w.x * tc.y;
+            }
+            if (m.bias_vis_off >= 0 && tid < 32) {                 // visible bias: Re(w) sum s, Im(w) sum s
+                int ssum = 0;
+                for (int i = tid; i < n; i += 32) ssum += sx[i];
+                for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+                if (tid == 0) {
+                    acc[m.bias_vis_off] += w.x * (float)ssum;
+                    acc[m.bias_vis_off + 1] += w.y * (float)ssum;
+                }
+            }
+        }
+        __syncthreads();
+        for (int l = D - 1; l >= 0; --l) {
+            const LayerInfo& L = m.layer[l];
+            const int ncog = L.coutp >> 2;
+            const float4* G4 = reinterpret_cast<const float4*>(G);
+            // ---- parameter gradients of layer l: one thread per (tap, C_in, 4 C_out) ----------------
+            const int ntask = k * k * L.cin * ncog;
+            for (int t = tid; t < ntask + L.cout; t += nthr) {
+                if (t >= ntask) {                                  // bias
+                    const int co = t - ntask;
+                    float sum = 0.f;
+                    for (int site = 0; site < n; ++site) sum += G[((co >> 2) * n + site) * 4 + (co & 3)];
+                    acc[L.b_off + co] += sum;
+                    continue;
+                }
+                const int cog = t % ncog, rest = t / ncog;
+                const int ci = rest % L.cin, d = rest / L.cin;
+                const int dy = d / k - p, dx = d % k - p;
+                const float* Ap = l == 0 ? A : A + (size_t)(ci >> 2) * n * 4 + (ci & 3);
+                const int astride = l == 0 ? 1 : 4;
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4* g = G4 + cog * n;
+                for (int y = 0; y < Ly; ++y) {
+                    const int qy = wrap1(y + dy, Ly) * Lx;
+                    for (int x = 0; x < Lx; ++x) {
+                        const float a = Ap[(qy + wrap1(x + dx, Lx)) * astride];
+                        const float4 gv = g[y * Lx + x];
+                        s4.x = fmaf(a, gv.x, s4.x); s4.y = fmaf(a, gv.y, s4.y);
+                        s4.z = fmaf(a, gv.z, s4.z); s4.w = fmaf(a, gv.w, s4.w);
+                    }
+                }
+                float* dst = acc + L.w_off + (d * L.cin + ci) * L.cout + cog * 4;
+                const int nco = min(4, L.cout - cog * 4);
+                if (nco > 0) dst[0] += s4.x;
+                if (nco > 1) dst[1] += s4.y;
+                if (nco > 2) dst[2] += s4.z;
+                if (nco > 3) dst[3] += s4.w;
+            }
+            // ---- cotangent of the layer below: one thread per (4 C_in, site) --------------------------
+            if (l > 0) {
+                const int ncig = L.cinp >> 2;
+                float4* Gn4 = reinterpret_cast<float4*>(Gn);
+                const float4* A4 = reinterpret_cast<const float4*>(A);
+                for (int t = tid; t < ncig * n; t += nthr) {
+                    const int cig = t / n, site = t - cig * n;
+                    const int y = site / Lx, x = site - y * Lx;
+                    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int dy = 0; dy < k; ++dy) {
+                        const int qy = wrap1(y - dy + p, Ly) * Lx;
+                        for (int dx = 0; dx < k; ++dx) {
+                            // output site q = site - (d - p) reads this input site through filter tap d
+                            const int q = qy + wrap1(x - dx + p, Lx);
+                            const float* wr = sp + L.sw_off + ((dy * k + dx) * L.cin + cig * 4) * L.coutp;
+                            for (int cg = 0; cg < ncog; ++cg) {
+                                const float4 gv = G4[cg * n + q];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (cig * 4 + j >= L.cin) break;
+                                    const float4 wv = *reinterpret_cast<const float4*>(wr + j * L.coutp + cg * 4);
+                                    sum[j] = fmaf(wv.x, gv.x, sum[j]); sum[j] = fmaf(wv.y, gv.y, sum[j]);
+                                    sum[j] = fmaf(wv.z, gv.z, sum[j]); sum[j] = fmaf(wv.w, gv.w, sum[j]);
+                                }
+                            }
+                        }
+                    }
+                    const float4 a = A4[cig * n + site];
+                    Gn4[cig * n + site] = make_float4((1.f - a.x * a.x) * sum[0], (1.f - a.y * a.y) * sum[1],
+                                                      (1.f - a.z * a.z) * sum[2], (1.f - a.w * a.w) * sum[3]);
+                }
+            }
+            __syncthreads();
+            if (l > 0) {
+                stage_input(l - 1);           // A is free: every thread is past the reads of this layer
+                float* tmp = G; G = Gn; Gn = tmp;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < m.P; i += blockDim.x) partial[(size_t)blockIdx.x * m.P + i] = acc[i];
+}
+
 __global__ void k_backward_reduce(const float* __restrict__ partial, int nparts, int P,
                                   float* __restrict__ grad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,8 +361,21 @@ __global__ void k_backward_reduce(const float* __restrict__ partial, int nparts,
     grad[i] += s;
 }
 
+static int gplane(const DevModel& m);
+
+// shared memory of k_backward_smem, or 0 when the planes do not fit / QMC_BACKWARD=generic
+static size_t backward_smem_bytes(const qmc_handle* h) {
+    const char* e = std::getenv("QMC_BACKWARD");           // "generic": force the L2-resident k_backward
+    if (e && std::strcmp(e, "generic") == 0) return 0;
+    const DevModel& m = h->m;
+    int c = 1;
+    for (int l = 0; l < m.D; ++l) c = c > m.layer[l].coutp ? c : m.layer[l].coutp;
+    const size_t bytes = (size_t)(m.smem_param_floats + round4(m.P) + 3 * round4(m.n * c)) * 4;
+    return bytes <= h->max_smem ? bytes : 0;
+}
+
 static int backward_ctas(const qmc_handle* h, int N) {
-    const int cap = h->num_sms * 2;
+    const int cap = backward_smem_bytes(h) ? h->num_sms : h->num_sms * 2;
     return N < cap ? (N > 0 ? N : 1) : cap;
 }
 
@@ -212,6 +400,19 @@ cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const floa
     float* partial = gscratch + (size_t)ctas * 2 * gplane(m);
     cudaError_t e = launch_forward(h, spins, N, cache, nullptr, nullptr, st, err);
     if (e != cudaSuccess) return e;
+    if (const size_t sb = backward_smem_bytes(h)) {
+        int c = 1;
+        for (int l = 0; l < m.D; ++l) c = c > m.layer[l].coutp ? c : m.layer[l].coutp;
+        e = cudaFuncSetAttribute(k_backward_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+        if (e != cudaSuccess) return e;
+        g_launches += 2;
+        k_backward_smem<<<ctas, kBwdSmemThreads, sb, st>>>(m, h->d_params, spins, reinterpret_cast<const float2*>(weights),
+                                                         N, cache, partial, round4(m.n * c));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        k_backward_reduce<<<(m.P + 127) / 128, 128, 0, st>>>(partial, ctas, m.P, grad);
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)(m.smem_param_floats + round4(m.P)) * 4;
     if (smem > h->max_smem) { err = "backward: parameters do not fit in shared memory"; return cudaErrorInvalidValue; }
     e = cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -479,3 +479,34 @@ def test_inplace_kernel_is_bit_identical_to_classic(layers, shape, S):
     ca, cb = a[5].view(S, cf), b[5].view(S, cf)
     used = cf - 2 * ((n + 3) // 4 * 4) + n          # everything up to and including fRe
     assert torch.equal(ca[:, :used], cb[:, :used])
+
+
+@pytest.mark.parametrize("kind,kw,shape", [("dcrbm", dict(layers=[16, 16, 16, 16, 16, 8]), (20, 20)),
+                                           ("dcrbm", dict(layers=[3, 5, 6]), (9, 8)),
+                                           ("dcrbm", dict(layers=[8, 8, 8]), (10, 10)),
+                                           ("crbm", dict(k=5, alpha=4), (6, 7)),
+                                           ("dcrbm", dict(k=5, layers=[4, 2]), (11, 10))])
+def test_shared_memory_backward_matches_generic_and_oracle(kind, kw, shape):
+    """k_backward_smem (planes staged in shared memory) against k_backward (QMC_BACKWARD=generic) and
+    against the oracle's autograd gradient of loss_op."""
+    import oracle
+    from gpu_util import make_pair, rand_states, padded
+    q = _q()
+    N = 37
+    gm, om = make_pair(kind, shape[0], 1e-1, 31, **kw)
+    rng = np.random.default_rng(8)
+    states = rand_states(rng, N, shape)
+    e = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    w = torch.as_tensor(((e - e.mean()) / N).astype(np.complex64), device="cuda")
+    grads = {}
+    for mode in ("generic", "smem"):
+        if mode == "generic":
+            os.environ["QMC_BACKWARD"] = "generic"
+        try:
+            grads[mode] = q.logpsi_gradient(gm, torch.as_tensor(states, device="cuda"), w, system_shape=shape).cpu().numpy()
+        finally:
+            os.environ.pop("QMC_BACKWARD", None)
+    scale = np.abs(grads["generic"]).max()
+    assert np.abs(grads["smem"] - grads["generic"]).max() <= 2e-6 * scale
+    want, _ = oracle.vmc_gradient(om.astype(np.float64), padded(om, states, shape), e)
+    assert np.abs(grads["smem"] - want).max() <= 1e-4 * np.abs(want).max()
