@@ -308,7 +308,9 @@ def run_cuda(args, cfg, name):
     l0 = _lib.load().qmc_launch_count()
     sampler._sweep(0, its)
     sweep_launches = int(_lib.load().qmc_launch_count() - l0)
-    # the classic persistent kernel is always ONE launch; more than one means the in-place kernel, time-sliced
+    # the probe counts the parameter repack + the sweep launches: the classic persistent kernel is always ONE
+    # launch; more than one means the in-place kernel, time-sliced
+    sweep_launches = max(sweep_launches - 1, 1)
     sweep_kernel = "k_sweep_ip" if sweep_launches > 1 else "k_sweep / k_sweep_ip (single launch: chains <= warp slots)"
     sync()
     clocks = ClockSampler(local_rank) if rank == 0 else None
