@@ -14,10 +14,11 @@ from .models import CRBM, DCRBM
 from .sampler import Sampler
 from . import distributed, symmetry
 from .symmetry import SymmetrizedModel
+from .vmc import run_vmc
 from .mcmc import (ising_energy, heisenberg_energy, batched_op, loss_op, optimize_op, eval_op,
                    logpsi_gradient, AdamTF1, OptimizeStep)
 
 __all__ = ["QmcError", "load_library", "LIB_PATH", "create_index_matrix", "scope_op", "pad", "unpad",
            "all_windows", "gather_windows", "update_windows", "interactions", "CRBM", "DCRBM",
            "Sampler", "SymmetrizedModel", "symmetry", "distributed", "ising_energy", "heisenberg_energy", "batched_op", "loss_op", "optimize_op",
-           "eval_op", "logpsi_gradient", "AdamTF1", "OptimizeStep"]
+           "eval_op", "logpsi_gradient", "AdamTF1", "OptimizeStep", "run_vmc"]

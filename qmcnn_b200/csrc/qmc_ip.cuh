@@ -81,12 +81,12 @@ __host__ __device__ inline int ip_sites_per_lane(int acc, int cout, int npos) {
     return pmax >= 8 ? 8 : 4;
 }
 
-// barrier of the warp's phase group: SYNC 1, 2 = the whole CTA; SYNC 3 = the four warps w/4 == g (one per
+// barrier of the warp's phase group: SYNC 2 = the whole CTA; SYNC 1, 3 = the four warps w/4 == g (one per
 // scheduler), so that an SM runs three phases at a time: few enough for the instruction caches, different
 // enough for the schedulers to overlap one group's memory latency with another group's arithmetic
 template <int SYNC>
 __device__ __forceinline__ void ip_barrier(int gid, int gthreads) {
-    if (SYNC == 3) asm volatile("bar.sync %0, %1;" ::"r"(gid), "r"(gthreads) : "memory");
+    if (SYNC == 3 || SYNC == 1) asm volatile("bar.sync %0, %1;" ::"r"(gid), "r"(gthreads) : "memory");
     else if (SYNC) __syncthreads();
 }
 

@@ -21,7 +21,7 @@ constexpr int kIpAcc = 64;            // accumulators per lane
 // is (4096 chains on 148 x 12 slots would otherwise be 2.3 waves = 77% efficiency).
 struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps; };
 
-// SYNC: 0 = warps run free; 1 = one CTA barrier per proposal; 2 = one per layer as well; 3 = per
+// SYNC: 0 = warps run free; 1 = phase-group barrier per proposal only; 2 = CTA barrier per layer; 3 = per
 // layer among the four warps of a phase group (ip_barrier).  With barriers the warps of a group
 // stay in the same phase of the proposal, so the SM's instruction working set is a few loop
 // bodies instead of twelve (the free-running version is instruction-fetch bound: 93% of the
