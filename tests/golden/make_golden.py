@@ -273,6 +273,9 @@ CASES = {
     # deep model, r = 7, on 8x8 with H = 3 (C2-like)
     "tfim_dcrbm": dict(model=("DCRBM", 3, (4, 4, 2), 2), system_shape=(8, 8), hamiltonian="tfim", H=3.0,
                        num_samples=8, num_flips=1, scale=0.3, seed=2003),
+    # a shape the in-place persistent kernel (k_sweep_ip) covers: 8 -> 8 hidden layers, k = 3, r = 7
+    "tfim_dcrbm888": dict(model=("DCRBM", 3, (8, 8, 8), 2), system_shape=(8, 8), hamiltonian="tfim", H=1.0,
+                          num_samples=8, num_flips=1, scale=0.2, seed=2006),
     # more samples than samplers: samples_per_sampler = 2, sample row order j * S + chain
     "tfim_crbm_sps2": dict(model=("CRBM", 5, 4, 2), system_shape=(6, 6), hamiltonian="tfim", H=1.0,
                            num_samples=8, num_flips=1, scale=0.1, seed=2004, max_num_samplers=4),
@@ -283,7 +286,10 @@ CASES = {
 
 
 def main():
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         case = dict(case)
         for attempt in range(20):
             single = run_case(case, "single")
@@ -307,6 +313,8 @@ def main():
             name, case["seed"], out["accept"].shape[0], out["accept"].shape[1], acc,
             float(np.real(out["energies"]).mean()),
             os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024))
+    if only:
+        return
     np.savez_compressed(os.path.join(HERE, "helpers.npz"), **helper_vectors())
     np.savez_compressed(os.path.join(HERE, "factors_nd.npz"), **factor_vectors())
     print("helpers.npz, factors_nd.npz written")

@@ -20,6 +20,7 @@ CASES = {
     "c1_tfim_crbm": dict(model=("CRBM", 5, 4, 2), shape=(6, 6), ham="tfim", H=1.0, num_samples=16, num_flips=1),
     "heis_crbm": dict(model=("CRBM", 5, 4, 2), shape=(6, 6), ham="heisenberg", H=1.0, num_samples=16, num_flips=2),
     "tfim_dcrbm": dict(model=("DCRBM", 3, (4, 4, 2), 2), shape=(8, 8), ham="tfim", H=3.0, num_samples=8, num_flips=1),
+    "tfim_dcrbm888": dict(model=("DCRBM", 3, (8, 8, 8), 2), shape=(8, 8), ham="tfim", H=1.0, num_samples=8, num_flips=1),
     "tfim_crbm_sps2": dict(model=("CRBM", 5, 4, 2), shape=(6, 6), ham="tfim", H=1.0, num_samples=8, num_flips=1,
                            max_num_samplers=4),
     "heis_dcrbm": dict(model=("DCRBM", 3, (4, 2), 2), shape=(6, 6), ham="heisenberg", H=1.0, num_samples=8,

@@ -50,8 +50,20 @@ def energy(case, model, states):
 SWEEPABLE = [n for n in sorted(CASES) if n != "heis_dcrbm"]
 
 
+@pytest.fixture(params=["default", "inplace", "pingpong", "batched"])
+def sweep_path(request):
+    """Every sweep decomposition must reproduce the reference's chains: the default choice, the in-place
+    persistent kernel forced on (k_sweep_ip; it is the default only for big models), the classic ping-pong
+    kernel, and the layer-synchronous batched kernels (each falls back to the classic kernel for shapes it
+    does not cover, e.g. CRBM or two flips)."""
+    if request.param != "default":
+        os.environ["QMC_SWEEP_PATH"] = request.param
+    yield request.param
+    os.environ.pop("QMC_SWEEP_PATH", None)
+
+
 @pytest.mark.parametrize("name", SWEEPABLE)
-def test_mcmc_op_reproduces_reference_chain(name):
+def test_mcmc_op_reproduces_reference_chain(name, sweep_path):
     case, g = CASES[name], load(name)
     model = build(case["model"], g)
     smp = make_sampler(case, model)
