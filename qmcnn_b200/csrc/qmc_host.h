@@ -21,8 +21,8 @@ struct qmc_handle {
     bool allow_lean = false;     // QMC_LEAN=1: lean persistent sweep kernel (more warps, smaller tiles); off by default
     bool allow_ip = true;        // QMC_SWEEP_PATH=pingpong disables the in-place persistent sweep kernel (k_sweep_ip)
     int ip_group = 4;            // QMC_IP_GROUP: warps per phase group of k_sweep_ip<3>
-    int ip_sync = 3;             // QMC_IP_SYNC: barriers of k_sweep_ip (0 none, 1 CTA per proposal, 2 CTA per layer,
-                                 // 3 = per layer within a phase group of ip_group warps - the default, fastest)
+    int ip_sync = 3;             // QMC_IP_SYNC: 0 = k_sweep_ip's warps run free, otherwise (default) a named barrier per
+                                 // layer within each phase group of ip_group warps
     bool force_ip = false;       // QMC_SWEEP_PATH=inplace: use k_sweep_ip whenever the model is inside its coverage
     bool allow_batched = true;  // QMC_FORCE_PERSISTENT=1 disables the layer-synchronous batched path (energy + sweep)
     bool batched_sweep = false; // QMC_SWEEP_PATH=batched: use the batched path for the sweep too (default: persistent

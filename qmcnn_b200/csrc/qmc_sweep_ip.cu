@@ -263,7 +263,9 @@ IpLaunch ip_launch_plan(const qmc_handle* h, int S) {
 
 cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st) {
     const int sy = h->ip_sync;
-    auto kern = sy == 3 ? k_sweep_ip<3> : sy == 2 ? k_sweep_ip<2> : sy == 1 ? k_sweep_ip<1> : k_sweep_ip<0>;
+    // two instances are built: free-running (QMC_IP_SYNC=0, diagnosis) and phase groups (default).  Per-proposal
+    // group barriers (1) and CTA-wide per-layer barriers (2) were measured (profiles/r01_summary.md) and dropped.
+    auto kern = sy == 0 ? k_sweep_ip<0> : k_sweep_ip<3>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e != cudaSuccess) return e;
     const long long slots = (long long)L.grid * L.warps;
