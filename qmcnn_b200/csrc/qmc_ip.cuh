@@ -19,7 +19,27 @@ __device__ __noinline__ float4 ip_tanh4(float4 a) {
 // sum_c Re log 2cosh(theta_c + i theta_{c+half}) of one site (site_factor<false> without the CRBM term)
 __device__ __noinline__ float ip_site_re(const float* th, int npos, int pos, int half) {
     float re = 0.f;
-    for (int c = 0; c < half; ++c) {
+    // four channels at a time: the loads first, then four independent exp / sincos / log chains the
+    // scheduler can interleave (one channel per iteration left this latency-bound at ILP 1); the sum
+    // keeps the order c = 0, 1, 2, ... of site_factor
+    int c = 0;
+    for (; c + 4 <= half; c += 4) {
+        float a[4], b[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c1 = c + j, c2 = c1 + half;
+            a[j] = th[((c1 >> 2) * npos + pos) * 4 + (c1 & 3)];
+            b[j] = th[((c2 >> 2) * npos + pos) * 4 + (c2 & 3)];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float i1 = 0.f;
+            log2cosh_c<false>(a[j], b[j], r[j], i1);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) re += r[j];
+    }
+    for (; c < half; ++c) {
         const int c2 = c + half;
         const float a = th[((c >> 2) * npos + pos) * 4 + (c & 3)];
         const float b = th[((c2 >> 2) * npos + pos) * 4 + (c2 & 3)];
