@@ -510,3 +510,43 @@ def test_shared_memory_backward_matches_generic_and_oracle(kind, kw, shape):
     assert np.abs(grads["smem"] - grads["generic"]).max() <= 2e-6 * scale
     want, _ = oracle.vmc_gradient(om.astype(np.float64), padded(om, states, shape), e)
     assert np.abs(grads["smem"] - want).max() <= 1e-4 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("sync", ["3", "0"])
+def test_time_sliced_inplace_sweep_is_bit_identical_to_classic(sync):
+    """More chains than warp slots: k_sweep_ip is time-sliced by the host into full-wave launches (one chunk
+    of one chain per slot; the last launch is partial, idle warps shadow a chain without writing).  Forced
+    here with one warp per CTA (148 slots) and 333 chains; results must equal the single-launch classic kernel
+    bit for bit, including the sample write-out at chunk-internal steps and the acceptance count."""
+    from gpu_util import make_pair
+    q = _q()
+    layers, shape, S = [16, 16, 16, 16, 16, 8], (20, 20), 333
+    outs = []
+    for path in ("pingpong", "inplace"):
+        os.environ["QMC_SWEEP_PATH"] = path
+        os.environ["QMC_MAX_WARPS"] = "1"
+        os.environ["QMC_IP_SYNC"] = sync
+        try:
+            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 29, layers=layers)
+            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+            init = (np.random.default_rng(6).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+            smp = GS(gm, shape, 13, 2 * S, 1, seed=3, chain_id0=1000)
+            assert smp.sample_its == 1201                     # 18 chunks of 67 steps, 5994 tasks on 148 slots
+            smp.feed(initial_states=init)
+            launches0 = q.load_library().qmc_launch_count()
+            samples = smp.mcmc_op(trace=True)
+            launches = q.load_library().qmc_launch_count() - launches0
+            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
+                         smp.acceptance_count, launches, smp._cache.clone()))
+        finally:
+            for k in ("QMC_SWEEP_PATH", "QMC_MAX_WARPS", "QMC_IP_SYNC"):
+                os.environ.pop(k, None)
+    a, b = outs
+    assert b[5] > a[5] + 30, "the in-place run was not time-sliced (%d vs %d launches)" % (b[5], a[5])
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert a[4] == b[4] and 0 < a[4] < a[0].numel()
+    h = gm.handle(shape)
+    cf, n = h.cache_floats, shape[0] * shape[1]
+    used = cf - 2 * ((n + 3) // 4 * 4) + n
+    assert torch.equal(a[6].view(S, cf)[:, :used], b[6].view(S, cf)[:, :used])
