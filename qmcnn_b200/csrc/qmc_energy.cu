@@ -6,6 +6,8 @@
 // and running the full network on each, a warp evaluates each flipped
 // configuration incrementally against the sample's activation cache (filled by
 // K1) and accumulates exp(log_pop) in registers.
+#include <cstdlib>
+#include <cstring>
 #include "qmc_host.h"
 
 // Compiled twice like qmc_sweep.cu: QMC_MAXW=8 (255 registers) and 16 (128 registers).
@@ -20,7 +22,7 @@ namespace qmc {
 
 constexpr int kAcc = QMC_MAXW <= 8 ? 64 : 32;
 
-constexpr int kEnergyChunks = 8;   // site chunks per sample (warp tasks = N * chunks)
+constexpr int kEnergyChunks = 16;  // site chunks per sample (warp tasks = N * chunks)
 
 __global__ void __launch_bounds__(QMC_MAXW * 32, 1)
 K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
@@ -174,7 +176,20 @@ cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, c
     float2* partial = reinterpret_cast<float2*>(workspace + (size_t)N * m.cache_floats);
     cudaError_t e = launch_forward(h, spins, N, cache, nullptr, nullptr, st, err);
     if (e != cudaSuccess) return e;
-    if (!heis && h->allow_batched && batched_supported(h)) {
+    // QMC_ENERGY_PATH=inplace|batched|persistent picks the TFIM decomposition (all agree to rounding of the
+    // final sums); default: see below
+    const char* ep = std::getenv("QMC_ENERGY_PATH");
+    // default for TFIM: the in-place persistent kernel when the model is inside its coverage and big enough for
+    // it to be the sweep's choice too (49.7k vs 47.9k energies/s at C3), else the batched kernels, else the
+    // classic persistent kernel
+    const bool forced_ip = ep && std::strcmp(ep, "inplace") == 0;
+    const bool want_ip = forced_ip || (!ep && ip_launch_plan(h, 1 << 20).ok);
+    if (!heis && want_ip && energy_ip_supported(h)) {
+        e = launch_energy_ip(h, spins, N, cache, partial, nchunks, st);
+        if (e != cudaSuccess) return e;
+        return launch_energy_finish(h, spins, N, hamiltonian, field_h, partial, nchunks, e_loc, moments, st);
+    }
+    if (!heis && h->allow_batched && batched_supported(h) && !(ep && std::strcmp(ep, "persistent") == 0)) {
         // layer-synchronous batched evaluation of all N * n single-flip configurations
         float2* terms = partial + (size_t)N * nchunks;
         float* scratch = reinterpret_cast<float*>(terms + (size_t)N * m.n);

@@ -173,6 +173,9 @@ struct IpLaunch { IpPlan ip; int warps, grid; size_t smem; bool ok; };
 IpPlan ip_plan(const qmc_handle* h);
 IpLaunch ip_launch_plan(const qmc_handle* h, int S);
 cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st);
+bool energy_ip_supported(const qmc_handle* h);
+cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, const float* cache, float2* partial,
+                             int nchunks, cudaStream_t st);
 cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, double* drel, cudaStream_t st,
                              std::string& err);
 int sweep_sym_slots(const qmc_handle* h, int S, int num_flips, int nsym, EvalPlan* plan, WarpGrid* grid);

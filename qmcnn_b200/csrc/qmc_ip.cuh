@@ -50,6 +50,22 @@ __device__ __noinline__ float ip_site_re(const float* th, int npos, int pos, int
     return re;
 }
 
+// (Re, Im) sum_c log 2cosh(theta_c + i theta_{c+half}) of one site: site_factor<true> without the CRBM term,
+// one channel at a time in site_factor's order (the local-energy kernel needs the complex ratio)
+__device__ __noinline__ float2 ip_site_reim(const float* th, int npos, int pos, int half) {
+    float re = 0.f, im = 0.f;
+    for (int c = 0; c < half; ++c) {
+        const int c2 = c + half;
+        const float a = th[((c >> 2) * npos + pos) * 4 + (c & 3)];
+        const float b = th[((c2 >> 2) * npos + pos) * 4 + (c2 & 3)];
+        float r1, i1;
+        log2cosh_c<true>(a, b, r1, i1);
+        re += r1;
+        im += i1;
+    }
+    return make_float2(re, im);
+}
+
 // cp.async the cache values of the frame of half-widths (a, a+p] around the centre into the arena
 __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip, const float* __restrict__ plane,
                                                 int ncg, int n, int a, int p, unsigned mgW, int y0, int x0,
@@ -126,11 +142,15 @@ __device__ __forceinline__ void ip_scatter_layer(const DevModel& m, const LayerI
     }
 }
 
-template <int ACC, int SYNC>
+// SWEEP = true: the Metropolis kernel - new windows are also written to `staging` (and start their
+// speculative commit copy), only Re of the log-ratio is formed.  SWEEP = false: the local-energy kernel -
+// nothing is staged (the cache is read-only), Re and Im are formed (dim).
+template <int ACC, int SYNC, bool SWEEP = true>
 __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPlan& ip, const float* sp,
                                                   const unsigned* mg, float* arena, float* spt, const int8_t* spins_s,
                                                   const float* __restrict__ cache, float* staging,
-                                                  int site_f, int lane, int gid, int gthreads, float& dre) {
+                                                  int site_f, int lane, int gid, int gthreads, float& dre,
+                                                  float* dim_out = nullptr) {
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n, D = m.D;
     const int T = ip.T, TA = ip.tarea, c = ip.c;
     const int y0 = site_f / Lx, x0 = site_f - y0 * Lx;
@@ -163,7 +183,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                             [&](int pos, int y, int x, int cog, float4 a) {
                                 a = ip_tanh4(a);
                                 arena4[cog * TA + (y + o0) * T + (x + o0)] = a;
-                                stg4[cog * rarea + pos] = a;
+                                if (SWEEP) stg4[cog * rarea + pos] = a;
                             });
         stg += L.coutp * rarea;
         cp_async_wait_all();
@@ -187,7 +207,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
             auto out = [&](int pos, int y, int x, int cog, float4 a) {
                 a = ip_tanh4(a);
                 arena4[cog * TA + (y + o0) * T + (x + o0)] = a;
-                stg4[cog * rarea + pos] = a;
+                if (SWEEP) stg4[cog * rarea + pos] = a;
             };
             // all lanes have read the input tile: the inner frame may land now, under the tanh epilogue
             auto mid = [&] {
@@ -214,8 +234,10 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
     if (SYNC >= 2) ip_barrier<SYNC>(gid, gthreads);
     // commit, part 1 (speculative): the staged windows of the first layers start their way from L2 into the
     // free part of the arena now, so that an accepted move finds them in shared memory after the head
-    for (int i = lane * 4; i < ip.spec_floats; i += kWarp * 4) cp_async16(arena + ip.spec_off + i, staging + i);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (SWEEP) {
+        for (int i = lane * 4; i < ip.spec_floats; i += kWarp * 4) cp_async16(arena + ip.spec_off + i, staging + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     // head over the last window: same lane ownership and order as warp_eval_flip
     const int npos = side * side, ry = y0 - D * p, rx = x0 - D * p;
     float* newf = arena + ip.newf_off;
@@ -223,26 +245,35 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
     // old factors first (their L2 latency overlaps the transcendental work); lane k owns the window
     // sites == k (mod 32) in increasing order, like warp_eval_flip; the host checks npos <= 8 * 32
     const int half = m.layer[D - 1].cout >> 1;
-    float ore[8];
+    float ore[8], oim[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int pos = j * kWarp + lane;
-        ore[j] = 0.f;
+        ore[j] = oim[j] = 0.f;
         if (pos < npos) {
             const int y = drw.div(pos), x = pos - y * side;
-            ore[j] = __ldcg(cache + m.fre_off + wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx));
+            const int site = wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx);
+            ore[j] = __ldcg(cache + m.fre_off + site);
+            if (!SWEEP) oim[j] = __ldcg(cache + m.fim_off + site);
         }
     }
-    float sre = 0.f;
+    float sre = 0.f, sim = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int pos = j * kWarp + lane;
         if (pos < npos) {
-            const float re = ip_site_re(arena, npos, pos, half);
-            newf[pos] = re;
-            sre += re - ore[j];
+            if (SWEEP) {
+                const float re = ip_site_re(arena, npos, pos, half);
+                newf[pos] = re;
+                sre += re - ore[j];
+            } else {
+                const float2 f = ip_site_reim(arena, npos, pos, half);
+                sre += f.x - ore[j];
+                sim += f.y - oim[j];
+            }
         }
     }
+    if (!SWEEP) *dim_out = warp_sum(sim);
     dre = warp_sum(sre);
     __syncwarp();
 }

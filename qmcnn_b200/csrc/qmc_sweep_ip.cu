@@ -293,4 +293,98 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
     return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_energy_ip: TFIM local energies (ising_energy, mcmc_tf.py:59-90) with the same in-place evaluator.
+// Warp task = (sample, chunk of sites): every single-flip configuration of the chunk is evaluated
+// against the sample's read-only cache (K1), exp(log_pop) is accumulated in registers in site order
+// (the classic k_energy's order), k_energy_finish adds the diagonal term.  Nothing is staged or
+// committed.  Phase-group barriers as in k_sweep_ip: every warp runs the same number of tasks and
+// sites, surplus ones shadow a valid evaluation without writing.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
+k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
+            const float* __restrict__ cache_all, float2* __restrict__ partial, int nchunks, IpPlan ip,
+            int group_warps) {
+    extern __shared__ float4 smem4[];
+    float* smem_f = reinterpret_cast<float*>(smem4);
+    load_params_to_smem(m, params, smem_f);
+    const float* sp = smem_f;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned* mg = reinterpret_cast<unsigned*>(smem_f + m.smem_param_floats);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < QMC_MAX_LAYERS; ++j) mg[j] = ip.mgW[j];
+    }
+    __syncthreads();
+    char* wmem = reinterpret_cast<char*>(mg + QMC_MAX_LAYERS) + (size_t)warp * ip.per_warp_bytes;
+    float* arena = reinterpret_cast<float*>(wmem);
+    float* spt = arena + ip.arena_floats;
+    int8_t* spins_s = reinterpret_cast<int8_t*>(spt + ip.spt_floats);
+    const int n = m.n;
+    const int g = warp / group_warps, gid = 1 + g, gthreads = 32 * min(group_warps, nwarps - g * group_warps);
+    const int cs = (n + nchunks - 1) / nchunks;
+    const long long ntasks = (long long)N * nchunks;
+    const long long slot = (long long)blockIdx.x * nwarps + warp, nslots = (long long)gridDim.x * nwarps;
+    int loaded = -1;
+    for (long long t0 = 0; t0 < ntasks; t0 += nslots) {         // the same trip count for every warp
+        const long long task = t0 + slot;
+        const bool has_task = task < ntasks;
+        const long long tt = has_task ? task : ntasks - 1;
+        const int s = (int)(tt / nchunks), chunk = (int)(tt - (long long)s * nchunks);
+        if (s != loaded) {
+            __syncwarp();
+            for (int i = lane; i < n; i += kWarp) spins_s[i] = spins[(size_t)s * n + i];
+            __syncwarp();
+            loaded = s;
+        }
+        const float* cache = cache_all + (size_t)s * m.cache_floats;
+        float are = 0.f, aim = 0.f;
+        const int i0 = chunk * cs, i1 = min(n, i0 + cs);
+        for (int ii = 0; ii < cs; ++ii) {
+            const bool active = i0 + ii < i1;
+            const int i = active ? i0 + ii : i1 - 1;
+            float dre, dim, sn, cn;
+            ip_barrier<3>(gid, gthreads);
+            warp_eval_flip_ip<kIpAcc, 3, false>(m, ip, sp, mg, arena, spt, spins_s, cache, nullptr, i, lane, gid,
+                                                gthreads, dre, &dim);
+            if (!active) continue;
+            const float amp = expf(dre);
+            sincosf(dim, &sn, &cn);
+            are += amp * cn;               // exp(log_pop), mcmc_tf.py:88
+            aim += amp * sn;
+        }
+        if (has_task && lane == 0) partial[(size_t)s * nchunks + chunk] = make_float2(are, aim);
+    }
+}
+
+// TFIM local energies through the in-place evaluator, if the model is inside its coverage
+bool energy_ip_supported(const qmc_handle* h) {
+    if (!h->allow_ip) return false;
+    const IpPlan ip = ip_plan(h);
+    if (!ip.ok) return false;
+    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + QMC_MAX_LAYERS * sizeof(unsigned);
+    return h->max_smem >= cta_bytes + (size_t)ip.per_warp_bytes;
+}
+
+cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, const float* cache, float2* partial,
+                             int nchunks, cudaStream_t st) {
+    const IpPlan ip = ip_plan(h);
+    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + QMC_MAX_LAYERS * sizeof(unsigned);
+    int w = (int)((h->max_smem - cta_bytes) / (size_t)ip.per_warp_bytes);
+    if (w > kIpMaxWarps) w = kIpMaxWarps;
+    if (h->max_warps_override > 0 && w > h->max_warps_override) w = h->max_warps_override;
+    const long long ntasks = (long long)N * nchunks;
+    if (ntasks < (long long)h->num_sms * w) w = (int)((ntasks + h->num_sms - 1) / h->num_sms);
+    const long long need = (ntasks + w - 1) / w;
+    const int grid = (int)(need < h->num_sms ? need : h->num_sms);
+    const size_t smem = cta_bytes + (size_t)ip.per_warp_bytes * w;
+    cudaError_t e = cudaFuncSetAttribute(k_energy_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ++g_launches;
+    k_energy_ip<<<grid, w * 32, smem, st>>>(h->m, h->d_params, spins, N, cache, partial, nchunks, ip,
+                                            h->ip_group > 0 ? h->ip_group : 4);
+    return cudaGetLastError();
+}
+
 } // namespace qmc

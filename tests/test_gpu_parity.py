@@ -550,3 +550,29 @@ def test_time_sliced_inplace_sweep_is_bit_identical_to_classic(sync):
     cf, n = h.cache_floats, shape[0] * shape[1]
     used = cf - 2 * ((n + 3) // 4 * 4) + n
     assert torch.equal(a[6].view(S, cf)[:, :used], b[6].view(S, cf)[:, :used])
+
+
+@pytest.mark.parametrize("layers,shape,N", [([16, 16, 16, 16, 16, 8], (20, 20), 5), ([8, 8, 8], (10, 10), 33),
+                                            ([16, 16, 8], (9, 8), 7), ([16, 8], (7, 9), 300)])
+def test_inplace_energy_kernel_matches_persistent_batched_and_oracle(layers, shape, N):
+    """k_energy_ip (TFIM local energies through the in-place evaluator, QMC_ENERGY_PATH=inplace) against the
+    classic persistent kernel (same per-chunk sums: equal bits), the batched kernels and the oracle."""
+    import oracle
+    from gpu_util import make_pair, rand_states
+    q = _q()
+    gm, om = make_pair("dcrbm", shape[0], 1e-1, 41, layers=layers)
+    states = rand_states(np.random.default_rng(12), N, shape)
+    st = torch.as_tensor(states, device="cuda")
+    out = {}
+    for path in ("inplace", "persistent", "batched"):
+        os.environ["QMC_ENERGY_PATH"] = path
+        try:
+            l0 = q.load_library().qmc_launch_count()
+            out[path] = q.ising_energy(gm, st, system_shape=shape, H=0.7).cpu().numpy()
+            out[path + "_launches"] = q.load_library().qmc_launch_count() - l0
+        finally:
+            os.environ.pop("QMC_ENERGY_PATH", None)
+    assert np.array_equal(out["inplace"], out["persistent"]), "in-place and classic persistent energies differ"
+    assert np.abs(out["inplace"] - out["batched"]).max() <= 2e-6 * np.abs(out["batched"]).max()
+    want = oracle.ising_energy(om.astype(np.float64), states, shape, om.r, H=0.7)
+    assert np.abs(out["inplace"] - want).max() <= 1e-5 * np.abs(want).max()
