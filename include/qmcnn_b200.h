@@ -106,7 +106,10 @@ int qmc_logpsi_forward(qmc_handle* h, const int8_t* spins, int N, float* cache,
  *           i >= therm_its, (i-therm_its) % its_per_sample == 0
  *           (sampler.py:135-152) and j < n_sample_slots (= samples_per_sampler)
  *   accept_trace [n_steps, S] uint8 or NULL; logratio_trace [n_steps, S] fp32
- *           (Re sum(f' - f)) or NULL; n_accept [1] uint64 (+=) or NULL. */
+ *           (Re sum(f' - f)) or NULL; n_accept [1] uint64 (+=) or NULL.
+ * The call enqueues one or more kernel launches on `stream` (deep models with more
+ * chains than resident warp slots are time-sliced into full-wave launches); which
+ * kernel runs never changes a result bit. */
 int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* workspace,
                          int S, int num_flips, int64_t step0, int64_t n_steps,
                          const int32_t* flip_pos, const float* uniforms,
