@@ -263,6 +263,33 @@ def factor_vectors():
     return out
 
 
+def symmetry_vectors():
+    """symmetry.ipynb cell 0, executed as it is (with the two numpy aliases its 2017-era code needs:
+    ``np.int`` and ``np.stack`` over a generator).  Its own assertions (group axioms, bijection,
+    neighbour preservation) run as part of the cell; cells 1-2 are evaluated too."""
+    import json
+    nb = json.load(open(os.path.join(REF, "symmetry.ipynb")))
+    src = ["".join(c["source"]) for c in nb["cells"] if c["cell_type"] == "code"]
+    if not hasattr(np, "int"):
+        np.int = int
+    orig_stack = np.stack
+    np.stack = lambda arrays, axis=0, **kw: orig_stack(list(arrays), axis, **kw)
+    ns = {}
+    try:
+        exec(compile(src[0], "symmetry.ipynb[0]", "exec"), ns)          # prints "Assertions succesful"
+        grid = eval("plot(mod(np.dot(D4[7], T[5])))", ns)                # cell 1
+        nb12 = eval("neighbours(grid)[12]", dict(ns, grid=grid))         # cell 2
+    finally:
+        np.stack = orig_stack
+    M = ns["M"]
+    out = {"M": np.array(M), "D4": np.asarray(ns["D4"]), "T": np.asarray(ns["T"]), "G": np.asarray(ns["G"]),
+           "plots": np.stack([ns["plot"](g) for g in ns["G"]]), "cell1_grid": np.asarray(grid),
+           "cell2_neighbours_12": np.asarray(nb12)}
+    idn = ns["neighbours"](ns["plot"](ns["T"][0]))
+    out["identity_neighbours"] = np.array([idn[i] for i in range(M * M)])
+    return out
+
+
 CASES = {
     # name: C1 of BASELINE.json (6x6 TFIM, CRBM(5,2,4,2)), sigma 0.1 so that acceptance is non-trivial
     "c1_tfim_crbm": dict(model=("CRBM", 5, 4, 2), system_shape=(6, 6), hamiltonian="tfim", H=1.0,
@@ -287,6 +314,9 @@ CASES = {
 
 def main():
     only = sys.argv[1:]
+    if only == ["symmetry"]:
+        np.savez_compressed(os.path.join(HERE, "symmetry.npz"), **symmetry_vectors())
+        return
     for name, case in CASES.items():
         if only and name not in only:
             continue
@@ -315,6 +345,7 @@ def main():
             os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024))
     if only:
         return
+    np.savez_compressed(os.path.join(HERE, "symmetry.npz"), **symmetry_vectors())
     np.savez_compressed(os.path.join(HERE, "helpers.npz"), **helper_vectors())
     np.savez_compressed(os.path.join(HERE, "factors_nd.npz"), **factor_vectors())
     print("helpers.npz, factors_nd.npz written")

@@ -168,3 +168,24 @@ def test_factors_in_1d_2d_3d():
         padded = oracle.pad(s, shape, [(model.r - 1) // 2] * len(shape))
         f = model.factors(padded)
         assert np.abs(f - g[tag + "/factors"]).max() <= 1e-10 * np.abs(g[tag + "/factors"]).max(), tag
+
+
+def test_symmetry_group_matches_reference_notebook():
+    """symmetry.ipynb cell 0 executed as it is (its assertions passed while recording): D4, T and G = D4 x T in
+    the notebook's element order, the site permutation `plot(g)` of every group element, the identity's
+    neighbour table, and cells 1-2 - reproduced by the oracle's and the product's group utilities."""
+    import qmcnn_b200.symmetry as ps
+    from oracle import symmetry as osym
+    g = np.load(os.path.join(GOLD, "symmetry.npz"))
+    M = int(g["M"])
+    for mod_ in (osym, ps):
+        assert np.array_equal(mod_.d4(M), g["D4"])
+        assert np.array_equal(mod_.translations(M), g["T"])
+        G = mod_.group(M)
+        assert np.array_equal(G, g["G"]) and len(G) == 8 * M * M
+        assert np.array_equal(np.stack([mod_.plot(x, M) for x in G]), g["plots"])
+        idn = mod_.neighbours(mod_.plot(mod_.translations(M)[0], M), M)
+        assert np.array_equal(np.array([idn[i] for i in range(M * M)]), g["identity_neighbours"])
+        grid = mod_.plot(mod_.mod(np.dot(mod_.d4(M)[7], mod_.translations(M)[5]), M), M)
+        assert np.array_equal(grid, g["cell1_grid"])
+        assert list(mod_.neighbours(grid, M)[12]) == list(g["cell2_neighbours_12"])
