@@ -149,6 +149,39 @@ int qmc_local_energy(qmc_handle* h, int hamiltonian, float field_h, const int8_t
 int qmc_logpsi_backward(qmc_handle* h, const int8_t* spins, const float* weights, int N,
                         float* workspace, float* grad, void* stream);
 
+/* ---- 1-D and 3-D lattices (models.py:56-61, 118-123: the conv1d / conv3d branches; sampler.py and
+ * mcmc_tf.py are n_dims-generic) ----------------------------------------------------------------------
+ * A separate, simple path: stateless entry points, one CTA per chain / sample running the reference's own
+ * algorithm (a full network evaluation per proposal / connected configuration).  `params` is the flat
+ * vector in the reference's variable order with filters [k]*n_dims + [C_in, C_out]; spins int8 +-1
+ * un-padded [N, prod(L)], row-major over the lattice axes.  n_dims = 2 is accepted too (cross-check of the
+ * tuned 2-D path).  The log-psi gradient is 2-D only. */
+typedef struct {
+    int32_t kind, k, n_layers;
+    int32_t channels[QMC_MAX_LAYERS];
+    int32_t n_dims;                   /* 1, 2 or 3 */
+    int32_t L[3];                     /* system_shape, first n_dims entries */
+    int32_t reserved[3];
+} qmc_nd_desc;
+const char* qmc_nd_last_error(void);
+size_t qmc_nd_num_params(const qmc_nd_desc* d);
+/* scratch floats for `units` chains / samples on `device` */
+size_t qmc_nd_scratch_floats(const qmc_nd_desc* d, int device, int units);
+/* model.factors / log psi: factors [N, n] complex64 or NULL, logpsi [N] complex64 or NULL */
+int qmc_nd_forward(const qmc_nd_desc* d, int device, const float* params, const int8_t* spins, int N,
+                   float* scratch, float* factors, float* logpsi, void* stream);
+/* Sampler.mcmc_step x n_steps (sampler.py:104-155); cur_factors [S, n] complex64 in/out must hold
+ * model.factors of `spins` under the current parameters (mcmc_reset, sampler.py:85-88); other arguments
+ * as qmc_metropolis_sweep */
+int qmc_nd_sweep(const qmc_nd_desc* d, int device, const float* params, int8_t* spins, float* cur_factors,
+                 float* scratch, int S, int num_flips, int64_t step0, int64_t n_steps, const int32_t* flip_pos,
+                 const float* uniforms, uint64_t seed, int64_t chain_id0, int64_t therm_its,
+                 int64_t its_per_sample, int8_t* samples, int64_t n_sample_slots, uint8_t* accept_trace,
+                 float* logratio_trace, unsigned long long* n_accept, void* stream);
+/* ising_energy / heisenberg_energy per spin (mcmc_tf.py:59-141), e_loc [N] complex64 */
+int qmc_nd_local_energy(const qmc_nd_desc* d, int device, int hamiltonian, float field_h, const float* params,
+                        const int8_t* spins, int N, float* scratch, float* e_loc, void* stream);
+
 /* Diagnostics (synchronous, not on the hot path): measured FP32-FMA (TFLOP/s)
  * and MUFU ex2 (Gop/s) issue peaks of `device` - the roofline denominators
  * MEASURED_PEAKS.json does not carry. */

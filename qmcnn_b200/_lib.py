@@ -25,6 +25,29 @@ class ModelDesc(C.Structure):
                 ("Ly", C.c_int32), ("Lx", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
+class NdDesc(C.Structure):
+    """include/qmcnn_b200.h: qmc_nd_desc (1-D / 3-D lattices)."""
+    _fields_ = [("kind", C.c_int32), ("k", C.c_int32), ("n_layers", C.c_int32),
+                ("channels", C.c_int32 * QMC_MAX_LAYERS), ("n_dims", C.c_int32),
+                ("L", C.c_int32 * 3), ("reserved", C.c_int32 * 3)]
+
+
+def nd_desc(kind, k, channels, shape):
+    d = NdDesc()
+    d.kind, d.k, d.n_layers, d.n_dims = kind, k, len(channels), len(shape)
+    for i, c in enumerate(channels):
+        d.channels[i] = c
+    for i, l in enumerate(shape):
+        d.L[i] = int(l)
+    return d
+
+
+def check_nd(rc, what):
+    if rc != 0:
+        msg = load().qmc_nd_last_error()
+        raise QmcError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
 # name -> (restype, argtypes); kept in one table so tests can check that every
 # symbol the header declares is exported and bound.
 _vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
@@ -49,6 +72,13 @@ SIGNATURES = {
                                       _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qmc_local_energy": (_i, [_vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "qmc_logpsi_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "qmc_nd_last_error": (C.c_char_p, []),
+    "qmc_nd_num_params": (_sz, [C.POINTER(NdDesc)]),
+    "qmc_nd_scratch_floats": (_sz, [C.POINTER(NdDesc), _i, _i]),
+    "qmc_nd_forward": (_i, [C.POINTER(NdDesc), _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "qmc_nd_sweep": (_i, [C.POINTER(NdDesc), _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,
+                          _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "qmc_nd_local_energy": (_i, [C.POINTER(NdDesc), _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_diag_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_diag_peaks2": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_launch_count": (C.c_ulonglong, []),

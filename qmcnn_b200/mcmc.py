@@ -40,6 +40,22 @@ def _local_energy(model, states, system_shape, hamiltonian, h_field, moments=Non
         shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
         fn = lambda im, st, system_shape: _local_energy(im, st, system_shape, hamiltonian, h_field)
         return model.local_energy(fn, states, shape)
+    if getattr(model, "n_dims", 2) != 2:
+        # 1-D / 3-D lattices: the generic path (one full network evaluation per connected configuration)
+        shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
+        d = model.nd_desc(shape)
+        st = torch.as_tensor(states, device=model.device).reshape(-1, int(np.prod(shape))).to(torch.int8).contiguous()
+        out = torch.empty(st.shape[0], dtype=torch.complex64, device=model.device)
+        if st.shape[0]:
+            scratch = model.nd_scratch(d, st.shape[0])
+            _lib.check_nd(_lib.load().qmc_nd_local_energy(
+                d, model.device.index or 0, hamiltonian, float(h_field), model.flat.data_ptr(), st.data_ptr(),
+                st.shape[0], scratch.data_ptr(), out.data_ptr(), _stream_ptr(model.device)), "qmc_nd_local_energy")
+        if moments is not None:
+            moments += torch.stack([torch.tensor(float(out.numel()), device=out.device, dtype=torch.float64),
+                                    out.real.double().sum(), out.imag.double().sum(),
+                                    (out.real.double() ** 2 + out.imag.double() ** 2).sum()])
+        return out
     states, system_shape, h = _prep(model, states, system_shape)
     N = states.shape[0]
     out = torch.empty(N, dtype=torch.complex64, device=model.device)
@@ -105,6 +121,8 @@ def logpsi_gradient(model, states, weights, system_shape=None, out=None):
             out.add_(g)
             return out
         return g
+    if getattr(model, "n_dims", 2) != 2:
+        raise _lib.QmcError("logpsi_gradient: the hand-written backward covers 2-D lattices only")
     states, system_shape, h = _prep(model, states, system_shape)
     N = states.shape[0]
     grad = torch.zeros(model.num_params, dtype=torch.float32, device=model.device) if out is None else out

@@ -47,8 +47,9 @@ class _Model(object):
     def handle(self, system_shape):
         """The library handle for this model on an Ly x Lx lattice, parameters synced."""
         system_shape = tuple(int(s) for s in system_shape)
-        if len(system_shape) != 2:
-            raise _lib.QmcError("the CUDA path covers 2-D lattices (n_dims == 2)")
+        if len(system_shape) != 2 or self.n_dims != 2:
+            raise _lib.QmcError("this call is covered by the tuned 2-D kernels only (n_dims == 2); 1-D / 3-D "
+                                "lattices have factors, Sampler and the energy estimators (qmc_nd_*)")
         h = self._handles.get(system_shape)
         if h is None:
             h = _lib.Handle(self._kind, self.k, self._channels, system_shape[0], system_shape[1],
@@ -58,6 +59,35 @@ class _Model(object):
         _lib.check(h.ptr, _lib.load().qmc_set_params(h.ptr, self.flat.data_ptr(),
                                                      _stream_ptr(self.device)), "qmc_set_params")
         return h
+
+    # ---- 1-D / 3-D lattices: the generic path (include/qmcnn_b200.h, qmc_nd_*) ------------
+    def nd_desc(self, system_shape):
+        system_shape = tuple(int(s) for s in system_shape)
+        if len(system_shape) != self.n_dims:
+            raise _lib.QmcError("system_shape %r does not have n_dims = %d axes" % (system_shape, self.n_dims))
+        d = _lib.nd_desc(self._kind, self.k, self._channels, system_shape)
+        if _lib.load().qmc_nd_num_params(d) != self.flat.numel():
+            raise _lib.QmcError("nd: parameter count mismatch: %s" % _lib.load().qmc_nd_last_error().decode())
+        return d
+
+    def nd_scratch(self, desc, units):
+        n = _lib.load().qmc_nd_scratch_floats(desc, self.device.index or 0, int(units))
+        return torch.empty(max(n, 4), dtype=torch.float32, device=self.device)
+
+    def nd_forward(self, spins, system_shape, want_factors=True, want_logpsi=False):
+        """factors / log psi of UN-padded states (N, prod(shape)) on a 1-D / 3-D (or 2-D) lattice."""
+        d = self.nd_desc(system_shape)
+        n = int(np.prod(system_shape))
+        spins = torch.as_tensor(spins, device=self.device).reshape(-1, n).to(torch.int8).contiguous()
+        N = spins.shape[0]
+        factors = torch.empty((N, n), dtype=torch.complex64, device=self.device) if want_factors else None
+        logpsi = torch.empty(N, dtype=torch.complex64, device=self.device) if want_logpsi else None
+        scratch = self.nd_scratch(d, N)
+        _lib.check_nd(_lib.load().qmc_nd_forward(
+            d, self.device.index or 0, self.flat.data_ptr(), spins.data_ptr(), N, scratch.data_ptr(),
+            factors.data_ptr() if want_factors else None, logpsi.data_ptr() if want_logpsi else None,
+            _stream_ptr(self.device)), "qmc_nd_forward")
+        return factors, logpsi
 
     # ---- forward ------------------------------------------------------------
     def _halo(self):
@@ -93,8 +123,20 @@ class _Model(object):
         x = torch.as_tensor(x, device=self.device)
         halo = self._halo()
         shape = tuple(int(s) - 2 * halo for s in x.shape[1:])
-        if len(shape) != 2 or min(shape) < 1:
-            raise _lib.QmcError("factors: expected (N, Ly+r-1, Lx+r-1) wrap-padded input")
+        if len(shape) != self.n_dims or min(shape) < 1:
+            raise _lib.QmcError("factors: expected (N,) + (L+r-1,)*n_dims wrap-padded input")
+        if self.n_dims != 2:
+            sl = (slice(None),) + tuple(slice(halo, halo + s) for s in shape)
+            inner = x[sl]
+            if check_periodic and halo:
+                img = inner
+                for ax, s in enumerate(shape):
+                    idx = torch.arange(-halo, s + halo, device=x.device) % s
+                    img = img.index_select(ax + 1, idx)
+                if not torch.equal(img, x):
+                    raise _lib.QmcError("factors: input is not a periodic (wrap-padded) image")
+            f, _ = self.nd_forward(inner.reshape(x.shape[0], -1), shape)
+            return f.view((x.shape[0],) + shape)
         inner = x[:, halo:halo + shape[0], halo:halo + shape[1]]
         if check_periodic and halo:
             iy = torch.arange(-halo, shape[0] + halo, device=x.device) % shape[0]
@@ -107,6 +149,8 @@ class _Model(object):
 
     def log_psi(self, spins, system_shape):
         """log psi of UN-padded states (N, Ly*Lx) -> complex64 (N,)."""
+        if self.n_dims != 2:
+            return self.nd_forward(spins, system_shape, want_factors=False, want_logpsi=True)[1]
         return self.forward_unpadded(spins, system_shape, want_factors=False, want_logpsi=True)[1]
 
 
@@ -114,12 +158,12 @@ class CRBM(_Model):
     """Convolutional marginalised RBM, ``models.py:6-67``."""
 
     def __init__(self, k, pad_size, alpha, n_dims, device=None, seed=None):
-        if n_dims != 2:
-            raise _lib.QmcError("the CUDA path covers n_dims == 2")
+        if n_dims not in (1, 2, 3):
+            raise _lib.QmcError("n_dims must be 1, 2 or 3")
         self.k, self.pad_size, self.alpha, self.n_dims = k, pad_size, alpha, n_dims
         self.r = k
         self._kind, self._channels = _lib.MODEL_CRBM, [2 * alpha]
-        self._init_params([("filters", (k, k, 1, 2 * alpha)), ("bias_vis", (2,)),
+        self._init_params([("filters", (k,) * n_dims + (1, 2 * alpha)), ("bias_vis", (2,)),
                            ("bias_hid", (2 * alpha,))], device, seed)
 
 
@@ -127,13 +171,13 @@ class DCRBM(_Model):
     """Deep convolutional marginalised RBM, ``models.py:70-131``."""
 
     def __init__(self, k, layers, n_dims, device=None, seed=None):
-        if n_dims != 2:
-            raise _lib.QmcError("the CUDA path covers n_dims == 2")
+        if n_dims not in (1, 2, 3):
+            raise _lib.QmcError("n_dims must be 1, 2 or 3")
         self.k, self.layers, self.n_dims = k, list(layers), n_dims
         self.r = len(self.layers) * (k - 1) + 1
         self._kind, self._channels = _lib.MODEL_DCRBM, list(layers)
         chans = [1] + self.layers
         specs = []
         for l, (cin, cout) in enumerate(zip(chans, chans[1:])):
-            specs += [("filters_%d" % l, (k, k, cin, cout)), ("bias_%d" % l, (cout,))]
+            specs += [("filters_%d" % l, (k,) * n_dims + (cin, cout)), ("bias_%d" % l, (cout,))]
         self._init_params(specs, device, seed)

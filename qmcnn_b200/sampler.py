@@ -52,6 +52,21 @@ class Sampler(object):
         self.chain_id0 = int(chain_id0)      # global id of chain 0 (rank offset under data parallelism)
         self.device = model.device
         S, n = self.num_samplers, self.num_spins
+        self._nd = getattr(model, "n_dims", 2) != 2       # 1-D / 3-D lattices: the generic path (qmc_nd_sweep)
+        if self._nd:
+            self._sym = False
+            self._desc = model.nd_desc(self.system_shape)
+            self._spins = torch.zeros((S, n), dtype=torch.int8, device=self.device)
+            self._factors = torch.zeros((S, n), dtype=torch.complex64, device=self.device)
+            self._scratch = model.nd_scratch(self._desc, S)
+            self._samples = torch.zeros((self.samples_per_sampler, S, n), dtype=torch.int8, device=self.device)
+            self._n_accept = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self.flip_positions_var = self.accept_sample_var = self._initial_states = None
+            self._step_base = 0
+            self._gen = torch.Generator(device=self.device)
+            self._gen.manual_seed(self.seed + 7919 * (self.chain_id0 + 1))
+            self.accept_trace = self.logratio_trace = None
+            return
         self._h = model.handle(self.system_shape)
         lib = _lib.load()
         from .symmetry import SymmetrizedModel
@@ -90,6 +105,8 @@ class Sampler(object):
     @property
     def current_factors_var(self):
         """complex64 [S, num_spins] (sampler.py:49-53), recomputed from the spins."""
+        if self._nd:
+            return self._factors
         m = self.model.base if self._sym else self.model
         return m.forward_unpadded(self._spins, self.system_shape)[0]
 
@@ -131,6 +148,10 @@ class Sampler(object):
             else:
                 self._spins.copy_(torch.randint(0, 2, self._spins.shape, generator=self._gen,
                                                 device=self.device, dtype=torch.int8) * 2 - 1)
+        if self._nd:
+            self._factors = self.model.nd_forward(self._spins, self.system_shape)[0]      # sampler.py:85-88
+            self._samples.zero_()
+            return
         if self._sym:
             # caches of the 8 images + relative log amplitudes from per-site factor differences
             S, cf = self.num_samplers, self._h.cache_floats
@@ -149,6 +170,8 @@ class Sampler(object):
         self._samples.zero_()
 
     def _sweep(self, step0, n_steps, trace=False):
+        if self._nd:
+            return self._sweep_nd(step0, n_steps, trace)
         h = self.model.handle(self.system_shape)
         fed = self.flip_positions_var is not None
         fp = ua = None
@@ -187,6 +210,29 @@ class Sampler(object):
             self.accept_trace.data_ptr() if trace else None,
             self.logratio_trace.data_ptr() if trace else None,
             self._n_accept.data_ptr(), _stream_ptr(self.device)), "qmc_metropolis_sweep")
+
+    def _sweep_nd(self, step0, n_steps, trace):
+        fed = self.flip_positions_var is not None
+        fp = ua = None
+        if fed:
+            if step0 + n_steps > self.flip_positions_var.shape[0]:
+                raise _lib.QmcError("fed-in proposals cover %d steps, need %d"
+                                    % (self.flip_positions_var.shape[0], step0 + n_steps))
+            fp = self.flip_positions_var[step0:step0 + n_steps]
+            ua = self.accept_sample_var[step0:step0 + n_steps]
+        S = self.num_samplers
+        if trace:
+            self.accept_trace = torch.zeros((n_steps, S), dtype=torch.uint8, device=self.device)
+            self.logratio_trace = torch.zeros((n_steps, S), dtype=torch.float32, device=self.device)
+        _lib.check_nd(_lib.load().qmc_nd_sweep(
+            self._desc, self.device.index or 0, self.model.flat.data_ptr(), self._spins.data_ptr(),
+            self._factors.data_ptr(), self._scratch.data_ptr(), S, self.num_flips,
+            step0 + (0 if fed else self._step_base), n_steps,
+            fp.data_ptr() if fed else None, ua.data_ptr() if fed else None, self.seed, self.chain_id0,
+            self.therm_its + (0 if fed else self._step_base), self.its_per_sample,
+            self._samples.data_ptr(), self.samples_per_sampler,
+            self.accept_trace.data_ptr() if trace else None, self.logratio_trace.data_ptr() if trace else None,
+            self._n_accept.data_ptr(), _stream_ptr(self.device)), "qmc_nd_sweep")
 
     @scope_op()
     def mcmc_step(self, i, trace=False):

@@ -1,0 +1,139 @@
+"""1-D and 3-D lattices (models.py:56-61 / 118-123 conv1d / conv3d branches; n_dims-generic sampler.py and
+mcmc_tf.py) through the generic CUDA path (qmc_nd_*): model.factors against the reference-run golden vectors,
+the sampler in lock-step with the oracle, both energy estimators against the oracle; n_dims = 2 factors
+through the same path are cross-checked against the golden vectors too."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import qmcnn_b200 as q
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TIE_BAND = 2e-5
+
+
+def pair(kind, n_dims, scale, seed, k=3, alpha=2, layers=(4, 4, 2), dtype=np.float32):
+    rng = np.random.default_rng(seed)
+    if kind == "crbm":
+        om = oracle.CRBM(k, (k - 1) // 2, alpha, n_dims, rng=rng, scale=scale, dtype=dtype)
+        gm = q.CRBM(k, (k - 1) // 2, alpha, n_dims, seed=0)
+    else:
+        om = oracle.DCRBM(k, list(layers), n_dims, rng=rng, scale=scale, dtype=dtype)
+        gm = q.DCRBM(k, list(layers), n_dims, seed=0)
+    gm.set_flat_params(om.flat_params().astype(np.float32))
+    return gm, om
+
+
+SPECS = {"crbm1d": ("CRBM", 3, 2, 1), "crbm2d": ("CRBM", 5, 4, 2), "crbm3d": ("CRBM", 3, 2, 3),
+         "dcrbm1d": ("DCRBM", 3, (4, 4, 2), 1), "dcrbm2d": ("DCRBM", 3, (4, 4, 2), 2), "dcrbm3d": ("DCRBM", 3, (4, 2), 3)}
+
+
+@pytest.mark.parametrize("tag", sorted(SPECS))
+def test_factors_match_reference_run_vectors(tag):
+    """model.factors in 1-D, 2-D and 3-D against what the reference's own models.py computed (float64)."""
+    g = np.load(os.path.join(GOLD, "factors_nd.npz"))
+    spec = SPECS[tag]
+    m = (q.CRBM(spec[1], (spec[1] - 1) // 2, spec[2], spec[3], seed=0) if spec[0] == "CRBM"
+         else q.DCRBM(spec[1], list(spec[2]), spec[3], seed=0))
+    m.set_flat_params(np.concatenate([g["%s/param/%s" % (tag, n)].ravel() for n in m.names]).astype(np.float32))
+    for n in m.names:
+        assert tuple(m.params[n].shape) == g["%s/param/%s" % (tag, n)].shape, n      # [k]*n_dims + [C_in, C_out]
+    s = torch.as_tensor(g[tag + "/spins"].astype(np.int32), device="cuda")
+    shape = tuple(s.shape[1:])
+    halo = (m.r - 1) // 2
+    x = q.pad(s, shape, [halo] * len(shape))
+    want = g[tag + "/factors"]
+    if m.n_dims == 2:          # the generic path on a 2-D lattice, and the tuned kernels
+        f_nd = m.nd_forward(s.reshape(s.shape[0], -1), shape)[0].view((-1,) + shape).cpu().numpy()
+        assert np.abs(f_nd - want).max() <= 1e-5 * np.abs(want).max()
+    f = m.factors(x).cpu().numpy()
+    assert f.shape == want.shape
+    assert np.abs(f - want).max() <= 1e-5 * np.abs(want).max()
+    lp = m.log_psi(s.reshape(s.shape[0], -1), shape).cpu().numpy()
+    assert np.abs(lp - want.reshape(want.shape[0], -1).sum(1)).max() <= 1e-5 * np.abs(want).sum(tuple(range(1, want.ndim))).max()
+    if halo:
+        bad = x.clone()
+        bad[(0,) + (0,) * len(shape)] *= -1          # a corner of the halo no longer matches its periodic image
+        with pytest.raises(q.QmcError):
+            m.factors(bad)
+
+
+@pytest.mark.parametrize("kind,shape,flips", [("crbm", (12,), 1), ("dcrbm", (11,), 1), ("crbm", (4, 3, 4), 1),
+                                              ("dcrbm", (5, 5, 5), 1), ("crbm", (10,), 2), ("crbm", (3, 4, 3), 2)])
+def test_sweep_lockstep_with_oracle(kind, shape, flips):
+    """Sampler.mcmc_op on fed-in randoms: every accept decision equals the float64 oracle's except inside the
+    float32 tie band; final states equal; sample write-out order as in sampler.py:135-152."""
+    n_dims, n = len(shape), int(np.prod(shape))
+    layers = (4, 4, 2) if n_dims == 1 else (4, 2)
+    gm, om = pair(kind, n_dims, 0.15 if kind == "crbm" else (0.7 if n_dims == 1 else 0.15), 5, layers=layers)
+    om64 = om.astype(np.float64)
+    S = 9
+    GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+    OS = type("OS", (oracle.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+    gs = GS(gm, shape, om.r, 2 * S, flips)
+    os64 = OS(om64, shape, om.r, 2 * S, flips)
+    n_steps = gs.sample_its
+    assert n_steps == os64.sample_its == 3 * n + 1
+    rng = np.random.default_rng(17)
+    init = (rng.integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+    pos = rng.integers(0, n, (n_steps, S, flips)).astype(np.int32)
+    if flips == 2:
+        pos[1, 0] = pos[1, 0, 0]
+    u = rng.random((n_steps, S)).astype(np.float32)
+    gs.feed(init, pos, u)
+    samples = gs.mcmc_op(trace=True)
+    acc = gs.accept_trace.cpu().numpy().astype(bool)
+    lr = gs.logratio_trace.cpu().numpy()
+    os64.mcmc_reset(init, pos, u)
+    ties = 0
+    for i in range(n_steps):
+        os64.mcmc_step(i, force_mask=acc[i])
+        t = os64.last_log_ratio.real
+        scale = np.maximum(1.0, np.abs(t))
+        ident = (pos[i, :, 0] == pos[i, :, 1]) if flips == 2 else np.zeros(S, bool)
+        assert (np.abs(lr[i] - t) / scale)[~ident].max() <= 2e-5
+        for c in np.nonzero(os64.last_own_mask != acc[i])[0]:
+            gap = abs(2.0 * float(t[c]) - np.log(max(float(u[i, c]), 1e-45))) / float(scale[c])
+            assert gap < TIE_BAND, "step %d chain %d: decisions differ outside the tie band (%g)" % (i, c, gap)
+            ties += 1
+    assert ties <= 2 and 0 < acc.sum() < acc.size
+    assert np.array_equal(gs.spins.cpu().numpy().astype(np.int32), os64.unpadded_current())
+    assert np.array_equal(samples.cpu().numpy(), os64.samples.reshape(2 * S, n))
+    assert np.array_equal(gs.current_samples_var.cpu().numpy(), os64.current_samples)
+    f = gs.current_factors_var.cpu().numpy()
+    assert np.abs(f - os64.current_factors).max() <= 2e-5 * max(1.0, np.abs(os64.current_factors).max())
+
+
+@pytest.mark.parametrize("kind,shape", [("crbm", (12,)), ("dcrbm", (11,)), ("crbm", (5, 6, 5)), ("dcrbm", (7, 7, 7))])
+def test_energies_match_oracle(kind, shape):
+    """Lattice sides are >= K + 2 (K = receptive field): below that the reference's window trick sees an unflipped
+    periodic image of a flipped site inside its (2K+1)-wide window (mcmc_tf.py:105-126) and no longer equals the
+    flipped lattice, which is what this path evaluates."""
+    n_dims, n = len(shape), int(np.prod(shape))
+    layers = (4, 4, 2) if n_dims == 1 else (4, 2)
+    gm, om = pair(kind, n_dims, 0.15 if kind == "crbm" else (0.7 if n_dims == 1 else 0.15), 9, layers=layers)
+    om64 = om.astype(np.float64)
+    states = (np.random.default_rng(3).integers(0, 2, (6 if n < 200 else 2, n)) * 2 - 1).astype(np.int32)
+    st = torch.as_tensor(states, device="cuda")
+    # 343 sites: every log-ratio is a float32 sum of 343 per-site differences of full-network factors (the
+    # reference's own formulation); measured 1.2e-5, the float32 oracle is no better
+    tol = 1e-5 if n < 200 else 3e-5
+    e = q.ising_energy(gm, st, system_shape=shape, H=0.8).cpu().numpy()
+    want = oracle.ising_energy(om64, states, shape, om.r, H=0.8)
+    assert np.abs(e - want).max() <= tol * np.abs(want).max()
+    e = q.heisenberg_energy(gm, st, system_shape=shape).cpu().numpy()
+    want = oracle.heisenberg_energy(om64, states, shape, om.r)
+    assert np.abs(e - want).max() <= tol * np.abs(want).max()
+    eb = q.batched_op(lambda s: q.heisenberg_energy(gm, s, system_shape=shape), st, st.shape[0] // 2).cpu().numpy()
+    assert np.array_equal(eb, e)
+
+
+def test_gradient_is_2d_only_and_says_so():
+    gm, _ = pair("crbm", 1, 0.1, 1)
+    with pytest.raises(q.QmcError):
+        q.logpsi_gradient(gm, torch.ones((2, 8), dtype=torch.int8, device="cuda"),
+                          torch.ones(2, dtype=torch.complex64, device="cuda"), (8,))
