@@ -155,7 +155,7 @@ int qmc_logpsi_backward(qmc_handle* h, const int8_t* spins, const float* weights
  * algorithm (a full network evaluation per proposal / connected configuration).  `params` is the flat
  * vector in the reference's variable order with filters [k]*n_dims + [C_in, C_out]; spins int8 +-1
  * un-padded [N, prod(L)], row-major over the lattice axes.  n_dims = 2 is accepted too (cross-check of the
- * tuned 2-D path).  The log-psi gradient is 2-D only. */
+ * tuned 2-D path). */
 typedef struct {
     int32_t kind, k, n_layers;
     int32_t channels[QMC_MAX_LAYERS];
@@ -181,6 +181,12 @@ int qmc_nd_sweep(const qmc_nd_desc* d, int device, const float* params, int8_t* 
 /* ising_energy / heisenberg_energy per spin (mcmc_tf.py:59-141), e_loc [N] complex64 */
 int qmc_nd_local_energy(const qmc_nd_desc* d, int device, int hamiltonian, float field_h, const float* params,
                         const int8_t* spins, int N, float* scratch, float* e_loc, void* stream);
+
+/* gradient of loss_op (mcmc_tf.py:35-56, 172-177): grad[P] += sum_n Re[w_n conj(d log psi_n / d p)],
+ * weights [N] complex64; deterministic */
+size_t qmc_nd_backward_scratch_floats(const qmc_nd_desc* d, int device, int N);
+int qmc_nd_logpsi_backward(const qmc_nd_desc* d, int device, const float* params, const int8_t* spins,
+                           const float* weights, int N, float* scratch, float* grad, void* stream);
 
 /* Diagnostics (synchronous, not on the hot path): measured FP32-FMA (TFLOP/s)
  * and MUFU ex2 (Gop/s) issue peaks of `device` - the roofline denominators

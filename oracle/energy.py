@@ -101,25 +101,27 @@ def vmc_gradient(model, samples_padded, energies, dtype=np.float64):
     names = model.names
     p = {n: torch.tensor(np.asarray(model.params[n], dtype=dtype), dtype=tdt,
                          requires_grad=True) for n in names}
-    x = torch.tensor(np.asarray(samples_padded), dtype=tdt)[:, None]   # NCHW
-    assert model.n_dims == 2, "gradient oracle restates the 2-D path only"
+    x = torch.tensor(np.asarray(samples_padded), dtype=tdt)[:, None]   # N, C, *spatial
+    nd = model.n_dims
+    convnd = (F.conv1d, F.conv2d, F.conv3d)[nd - 1]
+    bshape = (1, -1) + (1,) * nd
 
-    def conv(h, w):            # HWIO -> OIHW; F.conv2d is a cross-correlation
-        return F.conv2d(h, w.permute(3, 2, 0, 1))
+    def conv(h, w):            # [*k, I, O] -> [O, I, *k]; F.convNd is a cross-correlation
+        return convnd(h, w.permute([nd + 1, nd] + list(range(nd))))
 
     if hasattr(model, "alpha"):
         a = model.alpha
-        theta = conv(x, p["filters"]) + p["bias_hid"][None, :, None, None]
+        theta = conv(x, p["filters"]) + p["bias_hid"].reshape(bshape)
         theta = torch.complex(theta[:, :a], theta[:, a:])
         act = torch.log(torch.exp(theta) + torch.exp(-theta)).sum(1)
         ps = model.pad_size
-        xu = x[:, 0, ps:x.shape[2] - ps, ps:x.shape[3] - ps]
+        xu = x[(slice(None), 0) + tuple(slice(ps, x.shape[2 + d] - ps) for d in range(nd))]
         factors = act + torch.complex(p["bias_vis"][0] * xu, p["bias_vis"][1] * xu)
     else:
         h = x
         D = len(model.layers)
         for l in range(D):
-            h = conv(h, p["filters_%d" % l]) + p["bias_%d" % l][None, :, None, None]
+            h = conv(h, p["filters_%d" % l]) + p["bias_%d" % l].reshape(bshape)
             if l != D - 1:
                 h = torch.tanh(h)
         sep = model.layers[-1] // 2

@@ -79,6 +79,8 @@ SIGNATURES = {
     "qmc_nd_sweep": (_i, [C.POINTER(NdDesc), _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,
                           _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qmc_nd_local_energy": (_i, [C.POINTER(NdDesc), _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "qmc_nd_backward_scratch_floats": (_sz, [C.POINTER(NdDesc), _i, _i]),
+    "qmc_nd_logpsi_backward": (_i, [C.POINTER(NdDesc), _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_diag_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_diag_peaks2": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_launch_count": (C.c_ulonglong, []),

@@ -276,6 +276,135 @@ k_nd_energy(NdModel m, const float* __restrict__ params, const int8_t* __restric
     }
 }
 
+
+// flat site index of (site - tap + p): the output site that reads `site` through filter tap `tap`
+__device__ __forceinline__ int nd_neighbour_rev(const NdModel& m, int site, int tap) {
+    const int p = (m.k - 1) >> 1;
+    int q = 0, s = site, t = tap;
+#pragma unroll
+    for (int a = 2; a >= 0; --a) {
+        const int La = m.L[a];
+        const int c = s % La; s /= La;
+        int d = 0;
+        if (a >= 3 - m.nd) { d = p - t % m.k; t /= m.k; }
+        q += wrapi(c + d, La) * m.str[a];
+    }
+    return q;
+}
+
+__device__ __forceinline__ float2 nd_ctanh(float a, float b) {      // tanh(a + ib), stable (as qmc_backward.cu)
+    const float A = fabsf(a), e = expf(-2.f * A);
+    float sb, cb;
+    sincosf(b, &sb, &cb);
+    const float om = 1.f - e;
+    const float den = fmaf(om, om, 4.f * e * cb * cb);
+    return make_float2(copysignf((1.f - e * e) / den, a), 4.f * e * sb * cb / den);
+}
+
+// gradient of loss_op (mcmc_tf.py:35-56, 172-177) on 1-D / 3-D lattices: grad[p] += sum_n Re[w_n conj(d log psi_n / d p)].
+// One CTA per sample (grid-stride): forward with every layer's activations kept (global scratch), cotangent of
+// the last layer (Re, Im)(w conj tanh theta), real backprop; per-CTA accumulator in shared memory, one owner
+// thread per gradient element, fixed-order reduction over CTAs: deterministic.
+__global__ void __launch_bounds__(kNdThreads)
+k_nd_backward(NdModel m, const float* __restrict__ params, const int8_t* __restrict__ spins_all,
+              const float2* __restrict__ weights, int N, float* scratch, float* partial) {
+    extern __shared__ float acc[];
+    const int n = m.n, D = m.D;
+    for (int i = threadIdx.x; i < m.P; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const size_t plane = (size_t)n * m.cmax;
+    float* base = scratch + (size_t)blockIdx.x * ((size_t)(D + 2) * plane);
+    for (int s = blockIdx.x; s < N; s += gridDim.x) {
+        const int8_t* spins = spins_all + (size_t)s * n;
+        const float2 w = weights[s];
+        // forward, keeping act[l] = output of layer l (post-tanh for hidden layers, theta for the last)
+        for (int l = 0; l < D; ++l) {
+            const int cin = m.cin[l], cout = m.cout[l];
+            const float* in = l ? base + (size_t)(l - 1) * plane : nullptr;
+            float* out = base + (size_t)l * plane;
+            const float* wt = params + m.w_off[l];
+            for (int idx = threadIdx.x; idx < n * cout; idx += blockDim.x) {
+                const int site = idx / cout, co = idx - site * cout;
+                float a = __ldg(params + m.b_off[l] + co);
+                for (int tap = 0; tap < m.ktaps; ++tap) {
+                    const int q = nd_neighbour(m, site, tap);
+                    const float* wr = wt + (size_t)tap * cin * cout + co;
+                    if (l == 0) a = fmaf((float)spins[q], __ldg(wr), a);
+                    else for (int ci = 0; ci < cin; ++ci) a = fmaf(in[(size_t)q * cin + ci], __ldg(wr + ci * cout), a);
+                }
+                out[(size_t)site * cout + co] = l == D - 1 ? a : tanhf(a);
+            }
+            __syncthreads();
+        }
+        float* G = base + (size_t)D * plane;
+        float* Gn = G + plane;
+        {   // head cotangent
+            const int C = m.cout[D - 1], half = C >> 1;
+            const float* th = base + (size_t)(D - 1) * plane;
+            for (int t = threadIdx.x; t < n * half; t += blockDim.x) {
+                const int site = t / half, c = t - site * half;
+                const float2 tc = nd_ctanh(th[(size_t)site * C + c], th[(size_t)site * C + c + half]);
+                G[(size_t)site * C + c] = w.x * tc.x + w.y * tc.y;              // w * conj(t)
+                G[(size_t)site * C + c + half] = w.y * tc.x - w.x * tc.y;
+            }
+            if (m.bias_vis_off >= 0 && threadIdx.x == 0) {
+                int ssum = 0;
+                for (int i = 0; i < n; ++i) ssum += spins[i];
+                acc[m.bias_vis_off] += w.x * (float)ssum;
+                acc[m.bias_vis_off + 1] += w.y * (float)ssum;
+            }
+            __syncthreads();
+        }
+        for (int l = D - 1; l >= 0; --l) {
+            const int cin = m.cin[l], cout = m.cout[l];
+            const float* in = l ? base + (size_t)(l - 1) * plane : nullptr;
+            const int ntask = m.ktaps * cin * cout;
+            for (int t = threadIdx.x; t < ntask + cout; t += blockDim.x) {
+                if (t >= ntask) {
+                    const int co = t - ntask;
+                    float sum = 0.f;
+                    for (int site = 0; site < n; ++site) sum += G[(size_t)site * cout + co];
+                    acc[m.b_off[l] + co] += sum;
+                    continue;
+                }
+                const int co = t % cout, rest = t / cout, ci = rest % cin, tap = rest / cin;
+                float sum = 0.f;
+                for (int site = 0; site < n; ++site) {
+                    const int q = nd_neighbour(m, site, tap);
+                    const float a = l ? in[(size_t)q * cin + ci] : (float)spins[q];
+                    sum = fmaf(a, G[(size_t)site * cout + co], sum);
+                }
+                acc[m.w_off[l] + (tap * cin + ci) * cout + co] += sum;
+            }
+            if (l > 0) {
+                const float* wt = params + m.w_off[l];
+                for (int t = threadIdx.x; t < n * cin; t += blockDim.x) {
+                    const int site = t / cin, ci = t - site * cin;
+                    float sum = 0.f;
+                    for (int tap = 0; tap < m.ktaps; ++tap) {
+                        const int q = nd_neighbour_rev(m, site, tap);
+                        const float* wr = wt + ((size_t)tap * cin + ci) * cout;
+                        for (int co = 0; co < cout; ++co) sum = fmaf(__ldg(wr + co), G[(size_t)q * cout + co], sum);
+                    }
+                    const float a = in[(size_t)site * cin + ci];
+                    Gn[(size_t)site * cin + ci] = (1.f - a * a) * sum;
+                }
+            }
+            __syncthreads();
+            float* tmp = G; G = Gn; Gn = tmp;
+        }
+    }
+    for (int i = threadIdx.x; i < m.P; i += blockDim.x) partial[(size_t)blockIdx.x * m.P + i] = acc[i];
+}
+
+__global__ void k_nd_reduce(const float* __restrict__ partial, int nparts, int P, float* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * P + i];
+    grad[i] += s;
+}
+
 static thread_local std::string g_nd_err;
 
 static int nd_grid(int device, int units) {
@@ -373,6 +502,40 @@ int qmc_nd_local_energy(const qmc_nd_desc* d, int device, int hamiltonian, float
             m, params, spins, N, hamiltonian, field_h, scratch, reinterpret_cast<float2*>(e_loc));
     }
     ND_LEAVE("nd_local_energy");
+}
+
+size_t qmc_nd_backward_scratch_floats(const qmc_nd_desc* d, int device, int N) {
+    NdModel m;
+    std::string err;
+    if (!nd_build(d, m, err) || N < 1) return 0;
+    const size_t ctas = (size_t)nd_grid(device, N);
+    return ctas * ((size_t)(m.D + 2) * m.n * m.cmax + (size_t)m.P);
+}
+
+int qmc_nd_logpsi_backward(const qmc_nd_desc* d, int device, const float* params, const int8_t* spins,
+                           const float* weights, int N, float* scratch, float* grad, void* stream) {
+    ND_ENTER();
+    if (N > 0) {
+        if (!params || !spins || !weights || !scratch || !grad) {
+            g_nd_err = "nd_backward: null argument";
+            if (prev != device) cudaSetDevice(prev);
+            return QMC_ERR_BAD_ARGUMENT;
+        }
+        const int ctas = nd_grid(device, N);
+        float* partial = scratch + (size_t)ctas * ((size_t)(m.D + 2) * m.n * m.cmax);
+        const size_t smem = (size_t)m.P * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(k_nd_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            g_nd_err = "nd_backward: parameters do not fit in shared memory";
+            if (prev != device) cudaSetDevice(prev);
+            return QMC_ERR_UNSUPPORTED;
+        }
+        g_launches += 2;
+        k_nd_backward<<<ctas, kNdThreads, smem, (cudaStream_t)stream>>>(
+            m, params, spins, reinterpret_cast<const float2*>(weights), N, scratch, partial);
+        k_nd_reduce<<<(m.P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, ctas, m.P, grad);
+    }
+    ND_LEAVE("nd_backward");
 }
 
 } // extern "C"

@@ -121,8 +121,20 @@ def logpsi_gradient(model, states, weights, system_shape=None, out=None):
             out.add_(g)
             return out
         return g
-    if getattr(model, "n_dims", 2) != 2:
-        raise _lib.QmcError("logpsi_gradient: the hand-written backward covers 2-D lattices only")
+    if getattr(model, "n_dims", 2) != 2:          # 1-D / 3-D lattices: the generic path
+        shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
+        d = model.nd_desc(shape)
+        st = torch.as_tensor(states, device=model.device).reshape(-1, int(np.prod(shape))).to(torch.int8).contiguous()
+        grad = torch.zeros(model.num_params, dtype=torch.float32, device=model.device) if out is None else out
+        if st.shape[0]:
+            lib = _lib.load()
+            wts = weights.to(torch.complex64).contiguous()
+            ws = torch.empty(max(lib.qmc_nd_backward_scratch_floats(d, model.device.index or 0, st.shape[0]), 4),
+                             dtype=torch.float32, device=model.device)
+            _lib.check_nd(lib.qmc_nd_logpsi_backward(d, model.device.index or 0, model.flat.data_ptr(), st.data_ptr(),
+                                                     wts.data_ptr(), st.shape[0], ws.data_ptr(), grad.data_ptr(),
+                                                     _stream_ptr(model.device)), "qmc_nd_logpsi_backward")
+        return grad
     states, system_shape, h = _prep(model, states, system_shape)
     N = states.shape[0]
     grad = torch.zeros(model.num_params, dtype=torch.float32, device=model.device) if out is None else out
