@@ -176,7 +176,7 @@ def run_case(case, precision):
         energy_fn = lambda s: ref_mcmc.ising_energy(model, s)            # noqa: E731
     else:
         energy_fn = lambda s: ref_mcmc.heisenberg_energy(model, s)       # noqa: E731
-    if n_dims == 2:
+    if True:
         e = energy_fn(states).numpy()
         out["energies"] = e
         bs = case["num_samples"] // 2
@@ -303,6 +303,14 @@ CASES = {
     # a shape the in-place persistent kernel (k_sweep_ip) covers: 8 -> 8 hidden layers, k = 3, r = 7
     "tfim_dcrbm888": dict(model=("DCRBM", 3, (8, 8, 8), 2), system_shape=(8, 8), hamiltonian="tfim", H=1.0,
                           num_samples=8, num_flips=1, scale=0.2, seed=2006),
+    # 1-D and 3-D lattices: the conv1d / conv3d branches of models.py, the n_dims-generic sampler and estimators
+    # (lattice sides >= K + 2, so that the window trick of the energy functions sees no periodic image of a flip)
+    "tfim_crbm_1d": dict(model=("CRBM", 3, 2, 1), system_shape=(10,), hamiltonian="tfim", H=1.0,
+                         num_samples=8, num_flips=1, scale=0.3, seed=2007),
+    "heis_dcrbm_1d": dict(model=("DCRBM", 3, (4, 2), 1), system_shape=(9,), hamiltonian="heisenberg",
+                          num_samples=8, num_flips=2, scale=0.5, seed=2008),
+    "tfim_crbm_3d": dict(model=("CRBM", 3, 2, 3), system_shape=(5, 5, 5), hamiltonian="tfim", H=1.0,
+                         num_samples=4, num_flips=1, scale=0.2, seed=2009),
     # more samples than samplers: samples_per_sampler = 2, sample row order j * S + chain
     "tfim_crbm_sps2": dict(model=("CRBM", 5, 4, 2), system_shape=(6, 6), hamiltonian="tfim", H=1.0,
                            num_samples=8, num_flips=1, scale=0.1, seed=2004, max_num_samplers=4),

@@ -21,6 +21,9 @@ CASES = {
     "heis_crbm": dict(model=("CRBM", 5, 4, 2), shape=(6, 6), ham="heisenberg", H=1.0, num_samples=16, num_flips=2),
     "tfim_dcrbm": dict(model=("DCRBM", 3, (4, 4, 2), 2), shape=(8, 8), ham="tfim", H=3.0, num_samples=8, num_flips=1),
     "tfim_dcrbm888": dict(model=("DCRBM", 3, (8, 8, 8), 2), shape=(8, 8), ham="tfim", H=1.0, num_samples=8, num_flips=1),
+    "tfim_crbm_1d": dict(model=("CRBM", 3, 2, 1), shape=(10,), ham="tfim", H=1.0, num_samples=8, num_flips=1),
+    "heis_dcrbm_1d": dict(model=("DCRBM", 3, (4, 2), 1), shape=(9,), ham="heisenberg", H=1.0, num_samples=8, num_flips=2),
+    "tfim_crbm_3d": dict(model=("CRBM", 3, 2, 3), shape=(5, 5, 5), ham="tfim", H=1.0, num_samples=4, num_flips=1),
     "tfim_crbm_sps2": dict(model=("CRBM", 5, 4, 2), shape=(6, 6), ham="tfim", H=1.0, num_samples=8, num_flips=1,
                            max_num_samplers=4),
     "heis_dcrbm": dict(model=("DCRBM", 3, (4, 2), 2), shape=(6, 6), ham="heisenberg", H=1.0, num_samples=8,
@@ -91,7 +94,7 @@ def test_factors_and_energies(name):
         model = build_model(case["model"], g, dtype)
         r = model.r
         states = g["samples"].astype(np.int32)
-        padded = oracle.pad(states.reshape((-1,) + tuple(shape)), shape, [(r - 1) // 2] * 2)
+        padded = oracle.pad(states.reshape((-1,) + tuple(shape)), shape, [(r - 1) // 2] * len(shape))
         assert np.array_equal(padded[0], g["padded_samples_row0"])
         f = model.factors(padded)
         assert f.shape == g[pre + "factors"].shape
@@ -123,7 +126,8 @@ def test_two_optimisation_iterations(name):
         e = energy(case, model, samples)
         assert np.abs(e - g[pre + "energies"]).max() <= 1e-10 * np.abs(g[pre + "energies"]).max()
         r = model.r
-        padded = oracle.pad(samples.reshape((-1,) + tuple(case["shape"])), case["shape"], [(r - 1) // 2] * 2)
+        padded = oracle.pad(samples.reshape((-1,) + tuple(case["shape"])), case["shape"],
+                            [(r - 1) // 2] * len(case["shape"]))
         grad, _ = oracle.vmc_gradient(model, padded, e)
         want = np.concatenate([g[pre + "grad/" + n].ravel() for n in names])
         assert np.abs(grad - want).max() <= 1e-9 * np.abs(want).max()

@@ -100,7 +100,7 @@ def test_factors_and_energies(name):
     model = build(case["model"], g)
     shape, halo = case["shape"], (model.r - 1) // 2
     states = torch.as_tensor(g["samples"].astype(np.int32), device="cuda")
-    padded = q.pad(states.reshape((-1,) + tuple(shape)), shape, [halo, halo])
+    padded = q.pad(states.reshape((-1,) + tuple(shape)), shape, [halo] * len(shape))
     assert np.array_equal(padded[0].cpu().numpy(), g["padded_samples_row0"])
     f = model.factors(padded).cpu().numpy()
     assert f.shape == g["factors"].shape
