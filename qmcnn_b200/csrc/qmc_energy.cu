@@ -10,13 +10,19 @@
 #include <cstring>
 #include "qmc_host.h"
 
-// Compiled twice like qmc_sweep.cu: QMC_MAXW=8 (255 registers) and 16 (128 registers).
+// Compiled four times (Makefile): QMC_MAXW=8 (255 registers) / 16 (128 registers) like qmc_sweep.cu, times
+// QMC_HAM=0 (TFIM) / 1 (Heisenberg) - one Hamiltonian per translation unit, because ptxas needs minutes for a
+// kernel that inlines the evaluator for both (the clean build went from 6.5 to ~3 minutes).
 #ifndef QMC_MAXW
 #define QMC_MAXW 8
 #endif
+#ifndef QMC_HAM
+#define QMC_HAM 0
+#endif
 #define QMC_CAT2(a, b) a##b
 #define QMC_CAT(a, b) QMC_CAT2(a, b)
-#define K_ENERGY QMC_CAT(k_energy_w, QMC_MAXW)
+#define QMC_CAT4(a, b, c, d) QMC_CAT(QMC_CAT(a, b), QMC_CAT(c, d))
+#define K_ENERGY QMC_CAT4(k_energy_w, QMC_MAXW, _h, QMC_HAM)
 
 namespace qmc {
 
@@ -26,8 +32,9 @@ constexpr int kEnergyChunks = 16;  // site chunks per sample (warp tasks = N * c
 
 __global__ void __launch_bounds__(QMC_MAXW * 32, 1)
 K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
-         const float* __restrict__ cache_all, int hamiltonian, float2* __restrict__ partial,
+         const float* __restrict__ cache_all, float2* __restrict__ partial,
          int nchunks, EvalPlan pl, int allow_tiled) {
+    constexpr int hamiltonian = QMC_HAM;
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
     load_params_to_smem(m, params, smem_f);
@@ -91,22 +98,27 @@ K_ENERGY(DevModel m, const float* __restrict__ params, const int8_t* __restrict_
     }
 }
 
-cudaError_t QMC_CAT(launch_energy_main_w, QMC_MAXW)(const qmc_handle* h, const int8_t* spins, int N,
-                                                    const float* cache, int hamiltonian, float2* partial,
-                                                    int nchunks, const EvalPlan& pl, const WarpGrid& g,
-                                                    cudaStream_t st) {
+cudaError_t QMC_CAT4(launch_energy_main_w, QMC_MAXW, _h, QMC_HAM)(const qmc_handle* h, const int8_t* spins, int N,
+                                                                  const float* cache, float2* partial, int nchunks,
+                                                                  const EvalPlan& pl, const WarpGrid& g,
+                                                                  cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(K_ENERGY, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     ++g_launches;
-    K_ENERGY<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, spins, N, cache, hamiltonian, partial,
-                                                    nchunks, pl, h->allow_tiled ? 1 : 0);
+    K_ENERGY<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, spins, N, cache, partial, nchunks, pl,
+                                                    h->allow_tiled ? 1 : 0);
     return cudaGetLastError();
 }
 
-#if QMC_MAXW == 8
-cudaError_t launch_energy_main_w16(const qmc_handle* h, const int8_t* spins, int N, const float* cache,
-                                   int hamiltonian, float2* partial, int nchunks, const EvalPlan& pl,
-                                   const WarpGrid& g, cudaStream_t st);
+#if QMC_MAXW == 8 && QMC_HAM == 0
+#define QMC_DECL_ENERGY_MAIN(W, H)                                                                              \
+    cudaError_t launch_energy_main_w##W##_h##H(const qmc_handle* h, const int8_t* spins, int N, const float* cache, \
+                                               float2* partial, int nchunks, const EvalPlan& pl, const WarpGrid& g, \
+                                               cudaStream_t st);
+QMC_DECL_ENERGY_MAIN(8, 1)
+QMC_DECL_ENERGY_MAIN(16, 0)
+QMC_DECL_ENERGY_MAIN(16, 1)
+#undef QMC_DECL_ENERGY_MAIN
 
 // one thread per sample: ordered chunk sum, diagonal term, per-spin normalisation
 __global__ void k_energy_finish(DevModel m, const int8_t* __restrict__ spins, int N, int hamiltonian,
@@ -200,12 +212,16 @@ cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, c
     EvalPlan pl = eval_plan(m, h0, h0, true);
     WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, (long long)N * nchunks);
     if (!g.ok) { err = "local_energy: model does not fit in shared memory"; return cudaErrorInvalidValue; }
-    e = g.warps <= 8 ? launch_energy_main_w8(h, spins, N, cache, hamiltonian, partial, nchunks, pl, g, st)
-                     : launch_energy_main_w16(h, spins, N, cache, hamiltonian, partial, nchunks, pl, g, st);
+    if (heis)
+        e = g.warps <= 8 ? launch_energy_main_w8_h1(h, spins, N, cache, partial, nchunks, pl, g, st)
+                         : launch_energy_main_w16_h1(h, spins, N, cache, partial, nchunks, pl, g, st);
+    else
+        e = g.warps <= 8 ? launch_energy_main_w8_h0(h, spins, N, cache, partial, nchunks, pl, g, st)
+                         : launch_energy_main_w16_h0(h, spins, N, cache, partial, nchunks, pl, g, st);
     if (e != cudaSuccess) return e;
     return launch_energy_finish(h, spins, N, hamiltonian, field_h, partial, nchunks, e_loc, moments, st);
 }
 
-#endif // QMC_MAXW == 8
+#endif // QMC_MAXW == 8 && QMC_HAM == 0
 
 } // namespace qmc
