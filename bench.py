@@ -409,6 +409,9 @@ def run_cuda(args, cfg, name):
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "algorithmic_bytes_per_proposal": work["window_bytes"] * (1 + accept_rate)},
             "mufu_gops_peak": mufu.value,
+            "note": "bound is the FP32 FMA pipe of the CUDA cores (SURVEY.md section 8d: C <= 16 channels and fp32 "
+                    "parity rule out tensor cores; the per-proposal window is served from L2/HBM at ~0.14 of the HBM "
+                    "roofline, reported under 'hbm'); 'achieved' = algorithmic FLOP / sweep time",
             "traffic": None,
         }
         roofline["sweep_kernel_launches_per_step"] = sweep_launches
