@@ -577,3 +577,48 @@ def test_inplace_energy_kernel_matches_persistent_batched_and_oracle(layers, sha
     assert np.abs(out["inplace"] - out["batched"]).max() <= 2e-6 * np.abs(out["batched"]).max()
     want = oracle.ising_energy(om.astype(np.float64), states, shape, om.r, H=0.7)
     assert np.abs(out["inplace"] - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_full_size_c5_shapes():
+    """BASELINE C5 shapes (40x40, DCRBM k3 [16]*5+[8]): the in-place sweep (11 warps per SM at this lattice size),
+    k_energy_ip and the generic backward (the shared-memory planes do not fit 40x40) against the oracle and
+    against each other."""
+    from gpu_util import make_pair, rand_states, padded
+    q = _q()
+    shape, layers = (40, 40), [16, 16, 16, 16, 16, 8]
+    gm, om = make_pair("dcrbm", 40, 1e-1, 1301, layers=layers)
+    om64 = om.astype(np.float64)
+    rng = np.random.default_rng(4)
+    s = rand_states(rng, 6, shape)
+    st = torch.as_tensor(s, device="cuda")
+    # forward and translation invariance
+    lp = gm.log_psi(st, shape).cpu().numpy()
+    want = om64.log_psi(padded(om64, s, shape))
+    assert np.abs(lp - want).max() <= 1e-5 * np.abs(want).max()
+    # local energy of one sample against the oracle (1600 windows of 25 x 25 through the full network)
+    e = q.ising_energy(gm, st, system_shape=shape, H=1.0).cpu().numpy()
+    we = oracle.ising_energy(om64, s[:1], shape, om.r, H=1.0)
+    assert np.abs(e[:1] - we).max() <= ELOC_RTOL * np.abs(we).max()
+    # gradient (generic kernel at this size) against autograd
+    w = torch.as_tensor(((e - e.mean()) / len(e)).astype(np.complex64), device="cuda")
+    g = q.logpsi_gradient(gm, st, w, system_shape=shape).cpu().numpy()
+    wg, _ = oracle.vmc_gradient(om64, padded(om64, s, shape), e)
+    assert np.abs(g - wg).max() <= 1e-4 * np.abs(wg).max()
+    # sweep: in-place (default here) against the classic kernel, 1800 chains so that the in-place CTAs are full
+    S = 1800
+    init = rand_states(rng, S, shape)
+    outs = []
+    for path in ("pingpong", "inplace"):
+        os.environ["QMC_SWEEP_PATH"] = path
+        try:
+            gm2, _ = make_pair("dcrbm", 40, 1e-1, 1301, layers=layers)
+            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S))
+            smp = GS(gm2, shape, 13, S, 1, seed=9)
+            smp.feed(initial_states=init)
+            smp.mcmc_op(n_its=150, trace=True)
+            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone()))
+        finally:
+            os.environ.pop("QMC_SWEEP_PATH", None)
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert 0 < int(a[0].sum()) < a[0].numel()
