@@ -23,8 +23,8 @@ k_layer(const float* __restrict__ in_tiles, float* __restrict__ out, int n_items
         cp_async_wait_all();
         __syncwarp();
         float4* o4 = reinterpret_cast<float4*>(out + (size_t)item * rarea * COUT);
-        conv_region_tiled<3, 16, COUT, P>(wbase, bbase, tile, tw, tarea, rh, rw, lane,
-            [&](int pos, int, int, int cog, float4 a) {
+        conv_region_tiled<3, 16, COUT, P, true, 1>(wbase, bbase, nullptr, tile, 0, tw, tarea, rh, rw, lane,
+            [&](int, int pos, int, int, int cog, float4 a) {
                 a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
                 o4[cog * rarea + pos] = a;
             });
