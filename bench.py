@@ -48,7 +48,30 @@ CONFIGS = {
     "C5": dict(shape=(40, 40), kind="dcrbm", k=3, layers=[16, 16, 16, 16, 16, 8], chains=8192, H=1.0,
                ham="tfim", flips=1),
 }
-SCALE = 1e-2          # models.py:9,73
+SCALE = 1e-2          # models.py:9,73 (override: --sigma)
+
+
+def round4(v):
+    return (v + 3) & ~3
+
+
+def cache_mbytes(cfg, S):
+    """Per-GPU activation cache (qmc_cache_floats restated: hidden planes padded to 4 channels + fRe + fIm)."""
+    n = cfg["shape"][0] * cfg["shape"][1]
+    chans = [2 * cfg["alpha"]] if cfg["kind"] == "crbm" else list(cfg["layers"])
+    floats = sum(round4(c) * n for c in chans[:-1]) + 2 * round4(n)
+    return S * floats * 4 * (8 if cfg.get("sym") else 1) / 1e6
+
+
+def config_dict(name, cfg, S, world, sigma):
+    """`config` of the JSON line - identical for the CUDA arm and the reference arm."""
+    mb = cache_mbytes(cfg, S)
+    return {"workload": workload_name(name, dict(cfg, chains=S)), "chains_total": S * world, "sigma": sigma,
+            "l2": ("activation caches %.0f MB per GPU exceed the 126 MB L2 (inputs larger than L2); every "
+                   "step starts from a full forward that rewrites them" if mb > 126 else
+                   "activation caches %.0f MB per GPU fit the L2 and are not flushed: parity-test "
+                   "configuration, not the headline workload") % mb,
+            "step": "mcmc_op + local energies + moment allreduce + gradient + gradient allreduce + Adam"}
 
 
 def algorithmic_work(cfg):
@@ -101,18 +124,8 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def build_models(cfg, seed):
-    import oracle
-    rng = np.random.default_rng(seed)
-    if cfg["kind"] == "crbm":
-        om = oracle.CRBM(cfg["k"], (cfg["k"] - 1) // 2, cfg["alpha"], 2, rng=rng, scale=SCALE)
-    else:
-        om = oracle.DCRBM(cfg["k"], cfg["layers"], 2, rng=rng, scale=SCALE)
-    return om
-
-
-def flat_params(cfg, seed):
-    """Synthetic parameters ~N(0, SCALE) in the reference variable order (no oracle import)."""
+def flat_params(cfg, seed, sigma=SCALE):
+    """Synthetic parameters ~N(0, sigma) in the reference variable order (no oracle import)."""
     rng = np.random.default_rng(seed)
     k = cfg["k"]
     if cfg["kind"] == "crbm":
@@ -122,61 +135,85 @@ def flat_params(cfg, seed):
         shapes = []
         for a, b in zip(ch, ch[1:]):
             shapes += [(k, k, a, b), (b,)]
-    return np.concatenate([(SCALE * rng.standard_normal(s)).astype(np.float32).ravel() for s in shapes])
+    return np.concatenate([(sigma * rng.standard_normal(s)).astype(np.float32).ravel() for s in shapes])
 
 
-# ------------------------------------------------------------------------------ reference arm
-def run_reference(args, cfg, name):
-    """The reference algorithm on the host cores (torch-CPU restatement; TF cannot be installed).
-    Each step: a bounded sample of the workload - `ref_chains` chains x `ref_its` full-network
-    Metropolis iterations, then the window-trick local energy of `ref_energy` samples."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import oracle
-    from oracle import torch_ref
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    om = build_models(cfg, 1234)
-    tm = torch_ref.TorchModel(om)
-    Ly, Lx = cfg["shape"]
-    S, its, ne = args.ref_chains, args.ref_its, args.ref_energy
-    rng = np.random.default_rng(0)
-    states = torch.as_tensor((rng.integers(0, 2, (S, Ly, Lx)) * 2 - 1).astype(np.float32))
+# ------------------------------------------------------------------------------ reference algorithm on host cores
+class CpuReference(object):
+    """The reference algorithm (full network per proposal, sampler.py:117-133; window-trick local energy,
+    mcmc_tf.py:59-90) restated in torch-CPU (oracle/torch_ref.py; TensorFlow itself is not installable here) on a
+    BOUNDED sample of the workload: `chains` chains x `its` Metropolis iterations per step, then the local energy
+    of `ne` samples.  ONE code path for `--impl reference` and for the `cpu_baseline` leg of the CUDA arm."""
 
-    def step():
-        pos = torch.as_tensor(rng.integers(0, Ly * Lx, (its, S, cfg["flips"])).astype(np.int64))
-        u = torch.as_tensor(rng.random((its, S)).astype(np.float32))
+    NOTE = ("reference algorithm (full network per proposal, sampler.py:117-133) restated in torch-CPU "
+            "(oracle/torch_ref.py); TensorFlow itself is not installable here")
+
+    def __init__(self, cfg, sigma, chains=256, its=256, ne=4):
+        import oracle
+        from oracle import torch_ref
+        self.torch_ref, self.cfg = torch_ref, cfg
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        rng = np.random.default_rng(1234)
+        if cfg["kind"] == "crbm":
+            om = oracle.CRBM(cfg["k"], (cfg["k"] - 1) // 2, cfg["alpha"], 2, rng=rng, scale=sigma)
+        else:
+            om = oracle.DCRBM(cfg["k"], cfg["layers"], 2, rng=rng, scale=sigma)
+        self.tm = torch_ref.TorchModel(om)
+        self.S, self.its, self.ne = chains, its, ne
+        self.rng = np.random.default_rng(0)
+        Ly, Lx = cfg["shape"]
+        self.states = torch.as_tensor((self.rng.integers(0, 2, (chains, Ly, Lx)) * 2 - 1).astype(np.float32))
+
+    def step(self):
+        """Returns (seconds in the sweep, seconds in the energy)."""
+        cfg = self.cfg
+        Ly, Lx = cfg["shape"]
+        pos = torch.as_tensor(self.rng.integers(0, Ly * Lx, (self.its, self.S, cfg["flips"])).astype(np.int64))
+        u = torch.as_tensor(self.rng.random((self.its, self.S)).astype(np.float32))
         t0 = time.perf_counter()
-        cur, _ = torch_ref.metropolis_steps(tm, states, pos, u)
+        cur, _ = self.torch_ref.metropolis_steps(self.tm, self.states, pos, u)
         t1 = time.perf_counter()
-        if cfg["ham"] == "tfim":
-            torch_ref.ising_energy(tm, cur[:ne], H=cfg["H"])
+        if cfg["ham"] == "tfim" and self.ne:
+            self.torch_ref.ising_energy(self.tm, cur[:self.ne], H=cfg["H"])
         t2 = time.perf_counter()
         return t1 - t0, t2 - t1
 
-    for _ in range(args.warmup):
-        step()
-    ts, te = 0.0, 0.0
-    for _ in range(args.steps):
-        a, b = step()
-        ts += a
-        te += b
-    props = S * its * args.steps
-    value = props / ts
-    sample = "%d chains x %d full-network Metropolis its per step (of %d chains x %d its), energy on %d samples" % (
-        S, its, cfg["chains"], sample_its(cfg), ne)
+    def sample_text(self):
+        return "%d chains x %d full-network Metropolis its per step (of %d chains x %d its), energy on %d samples" % (
+            self.S, self.its, self.cfg["chains"], sample_its(self.cfg), self.ne)
+
+    def measure(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        ts = te = 0.0
+        for _ in range(steps):
+            a, b = self.step()
+            ts += a
+            te += b
+        value = self.S * self.its * steps / ts
+        return value, ts, te, {"value": value, "unit": "proposals/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": self.sample_text() + ", %d step(s)" % steps,
+                               "local_energies_per_s": (self.ne * steps / te) if te > 0 else None, "note": self.NOTE}
+
+
+def run_reference(args, cfg, name):
+    """`--impl reference`: the reference algorithm on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ref = CpuReference(cfg, args.sigma, args.ref_chains, args.ref_its, args.ref_energy)
+    value, ts, te, base = ref.measure(args.steps, args.warmup)
+    S = args.chains or cfg["chains"]
     line = {
         "impl": "reference", "metric": "metropolis_proposals_per_s", "value": value, "unit": "proposals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (ts + te) / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(name, cfg), "sample": sample},
-        "local_energies_per_s": (ne * args.steps / te) if te > 0 else None,
-        "cpu_baseline": {"value": value, "unit": "proposals/s", "cores": torch.get_num_threads(),
-                         "kind": "port", "sample": sample,
-                         "note": "reference algorithm restated in torch-CPU (oracle/torch_ref.py); "
-                                 "TensorFlow itself is not installable here"},
+        "config": config_dict(name, cfg, S, world, args.sigma),
+        "local_energies_per_s": base["local_energies_per_s"],
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -198,40 +235,12 @@ def workload_name(name, cfg):
 
 
 # ------------------------------------------------------------------------------ CUDA arm
-def cpu_baseline(cfg, budget_s=20.0):
-    """Bounded CPU sample of the same workload, rank 0, N=1 only."""
-    import oracle
-    from oracle import torch_ref
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    om = build_models(cfg, 1234)
-    tm = torch_ref.TorchModel(om)
-    Ly, Lx = cfg["shape"]
-    S = 256
-    rng = np.random.default_rng(0)
-    states = torch.as_tensor((rng.integers(0, 2, (S, Ly, Lx)) * 2 - 1).astype(np.float32))
-    its = 64
-    pos = torch.as_tensor(rng.integers(0, Ly * Lx, (its, S, cfg["flips"])).astype(np.int64))
-    u = torch.as_tensor(rng.random((its, S)).astype(np.float32))
-    torch_ref.metropolis_steps(tm, states, pos[:4], u[:4])          # warm-up
-    done, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s * 0.7:
-        torch_ref.metropolis_steps(tm, states, pos, u)
-        done += its * S
-    ts = time.perf_counter() - t0
-    ne, te, nd = 4, 0.0, 0
-    if cfg["ham"] == "tfim":
-        t1 = time.perf_counter()
-        while time.perf_counter() - t1 < budget_s * 0.3:
-            torch_ref.ising_energy(tm, states[:ne], H=cfg["H"])
-            nd += ne
-        te = time.perf_counter() - t1
-    return {"value": done / ts, "unit": "proposals/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d chains x %d full-network Metropolis its repeated for %.0f s; energy on %d samples for %.0f s"
-                      % (S, its, ts, ne, te),
-            "local_energies_per_s": (nd / te) if te > 0 else None,
-            "note": "reference algorithm (full network per proposal, sampler.py:117-133) restated in torch-CPU; "
-                    "TensorFlow itself is not installable here"}
+def algorithmic_work_total(cfg):
+    """Per proposal, incl. the symmetry images and the number of flipped sites (SURVEY 8d closed forms are per
+    single-site window of one network)."""
+    w = algorithmic_work(cfg)
+    mult = (8 if cfg.get("sym") else 1) * cfg["flips"]
+    return {k: v * mult for k, v in w.items()}
 
 
 def run_cuda(args, cfg, name):
@@ -257,7 +266,7 @@ def run_cuda(args, cfg, name):
         model = q.CRBM(cfg["k"], (cfg["k"] - 1) // 2, cfg["alpha"], 2, device=dev, seed=0)
     else:
         model = q.DCRBM(cfg["k"], cfg["layers"], 2, device=dev, seed=0)
-    params_host = torch.as_tensor(flat_params(cfg, 1234)).pin_memory()
+    params_host = torch.as_tensor(flat_params(cfg, 1234, args.sigma)).pin_memory()
     model.set_flat_params(params_host)
     base_model = model
     if cfg.get("sym"):
@@ -271,30 +280,9 @@ def run_cuda(args, cfg, name):
         energy_fn = lambda s: q.ising_energy(model, s, system_shape=(Ly, Lx), H=cfg["H"])
     else:
         energy_fn = lambda s: q.heisenberg_energy(model, s, system_shape=(Ly, Lx))
+    # the timed step IS the product's optimisation step (mcmc_tf.py:218-222): OptimizeStep.run()
     opt = q.optimize_op(sampler, model, energy_fn)
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    seg = {"sweep": 0.0, "energy": 0.0, "gradient": 0.0}
-
-    def step(timed):
-        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-        e0.record()
-        sampler.mcmc_op()
-        e1.record()
-        samples = sampler.samples_int8()
-        energies = energy_fn(samples)
-        mom = torch.stack([torch.tensor(float(S), device=dev, dtype=torch.float64),
-                           energies.real.double().sum(), energies.imag.double().sum()])
-        if world > 1:
-            dist.all_reduce(mom)
-        e2.record()
-        e_mean = torch.complex(mom[1] / mom[0], mom[2] / mom[0]).to(torch.complex64)
-        grad = q.logpsi_gradient(model, samples, (energies - e_mean) / mom[0].float(), (Ly, Lx))
-        if world > 1:
-            dist.all_reduce(grad)
-        opt.optimizer.step(grad)
-        e3.record()
-        return (e0, e1, e2, e3), energies
+    opt.record_events = True
 
     def sync():
         if world > 1:
@@ -302,32 +290,42 @@ def run_cuda(args, cfg, name):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step(False)
+        opt.run(new_samples=True)
     sync()
-    # launches of the sweep kernel in one mcmc_op (the reset forward is one more launch)
-    l0 = _lib.load().qmc_launch_count()
+    # kernels of the sweep segment of one step (library's own launch counter; the reset forward is part of mcmc_op)
+    lib = _lib.load()
+    l0 = lib.qmc_launch_count()
     sampler._sweep(0, its)
-    sweep_launches = int(_lib.load().qmc_launch_count() - l0)
-    # the probe counts the parameter repack + the sweep launches: the classic persistent kernel is always ONE
-    # launch; more than one means the in-place kernel, time-sliced
-    sweep_launches = max(sweep_launches - 1, 1)
-    sweep_kernel = "k_sweep_ip" if sweep_launches > 1 else "k_sweep / k_sweep_ip (single launch: chains <= warp slots)"
+    sweep_launches = max(int(lib.qmc_launch_count() - l0) - 1, 1)     # minus the parameter repack of handle()
+    if cfg.get("sym"):
+        sweep_kernel = "k_sweep_sym"
+    elif getattr(sampler, "_nd", False):
+        sweep_kernel = "k_nd_sweep"
+    elif cfg["kind"] == "dcrbm" and sweep_launches > 1:
+        sweep_kernel = "k_sweep_ip (time-sliced: one chunk of one chain per warp slot and launch)"
+    else:
+        sweep_kernel = "k_sweep_w8 / k_sweep_w16 / k_sweep_ip (single launch)"
     sync()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
     t_start, t_end = ev(), ev()
     sampler._n_accept.zero_()
-    launches0 = _lib.load().qmc_launch_count()
+    launches0 = lib.qmc_launch_count()
     sync()
     t_start.record()
-    marks = [step(True) for _ in range(args.steps)]
+    marks = []
+    for _ in range(args.steps):
+        last_e = opt.run(new_samples=True)
+        marks.append(opt.last_events)
     t_end.record()
     sync()
     clk = clocks.stop() if clocks else None
-    gpu_launches = int(_lib.load().qmc_launch_count() - launches0)     # counted by the library itself
+    gpu_launches = int(lib.qmc_launch_count() - launches0)     # counted by the library itself
     elapsed_ms = t_start.elapsed_time(t_end)
-    for (e0, e1, e2, e3), _ in marks:
+    seg = {"sweep": 0.0, "energy": 0.0, "gradient": 0.0}
+    for e0, e1, e2, e3 in marks:
         seg["sweep"] += e0.elapsed_time(e1)
         seg["energy"] += e1.elapsed_time(e2)
         seg["gradient"] += e2.elapsed_time(e3)
@@ -338,24 +336,25 @@ def run_cuda(args, cfg, name):
     proposals = float(S) * its * args.steps * world
     value = proposals / (elapsed_ms * 1e-3)
     accept_rate = sampler.acceptance_count / (float(S) * its * args.steps)
-    last_e = marks[-1][1]
     e_mean = float(last_e.real.mean())
     e_err = float(last_e.real.std() / np.sqrt(S))
 
-    # ---- end to end through the public API with host buffers (rank-local, all ranks run it)
+    # ---- end to end: the SAME step through the public API with HOST buffers: every step copies its inputs
+    # (parameters, initial lattices) from pinned host memory and reads its results (energies, updated
+    # parameters, samples) back
     host_init = torch.empty((S, n), dtype=torch.int8).pin_memory()
     host_init.copy_(torch.randint(0, 2, (S, n), dtype=torch.int8) * 2 - 1)
     host_samples = torch.empty((S, n), dtype=torch.int8).pin_memory()
     host_e = torch.empty(S, dtype=torch.complex64).pin_memory()
+    host_params_out = torch.empty_like(params_host).pin_memory()
 
     def e2e_step():
         base_model.flat.copy_(params_host, non_blocking=True)                  # H2D parameters
         sampler.feed(initial_states=host_init.to(dev, non_blocking=True))      # H2D lattices
-        sampler.new_samples = True
-        sampler.mcmc_op()
-        smp = sampler.samples_int8()
-        host_samples.copy_(smp, non_blocking=True)                             # D2H samples
-        host_e.copy_(energy_fn(smp), non_blocking=True)                        # D2H energies
+        energies = opt.run(new_samples=True)                                   # sample, E_loc, gradient, allreduces, Adam
+        host_samples.copy_(sampler.samples_int8(), non_blocking=True)          # D2H samples
+        host_e.copy_(energies, non_blocking=True)                              # D2H energies
+        host_params_out.copy_(base_model.flat, non_blocking=True)              # D2H updated parameters
         torch.cuda.current_stream().synchronize()
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step()
@@ -369,10 +368,8 @@ def run_cuda(args, cfg, name):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = float(S) * its * e2e_steps * world / float(e2e_s.item())
 
-    cache_mb = S * sampler._h.cache_floats * 4 * (8 if cfg.get("sym") else 1) / 1e6
     if rank == 0:
-        work = algorithmic_work(cfg)
-        lib = _lib.load()
+        work = algorithmic_work_total(cfg)
         import ctypes
         f32, f32x2, mufu = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
         lib.qmc_diag_peaks2(local_rank, ctypes.byref(f32), ctypes.byref(f32x2), ctypes.byref(mufu))
@@ -387,8 +384,8 @@ def run_cuda(args, cfg, name):
         # models that is k_sweep_ip, time-sliced by the host into full-wave launches (one chunk of one chain per
         # warp slot); total proposals / total time equals the launch-weighted mean of per-launch rates.
         sweep_s = sw_ms * 1e-3 / args.steps
-        props_per_launch = float(S) * its
-        ach_tflops = props_per_launch * work["flop"] / sweep_s * 1e-12
+        props_per_step = float(S) * its
+        ach_tflops = props_per_step * work["flop"] / sweep_s * 1e-12
         # which of the three rooflines bounds one proposal:
         # t = max(F / FP32_peak, T / MUFU_peak, B / HBM_peak); ~2 MUFU per tanh, ~5 per complex log-2cosh
         mufu_ops = 2.0 * work["tanh"] + 5.0 * work["logcosh"]
@@ -398,42 +395,42 @@ def run_cuda(args, cfg, name):
         bound = "fp32_fma" if t_f >= max(t_m, t_b) else ("mufu" if t_m >= t_b else "hbm")
         roofline = {
             "kernel": sweep_kernel, "bound": bound, "bound_times_ns": {"fp32": t_f * 1e9, "mufu": t_m * 1e9, "hbm": t_b * 1e9},
-            "frac_of_bound": max(t_f, t_m, t_b) / (sweep_s / props_per_launch),
+            "frac_of_bound": max(t_f, t_m, t_b) / (sweep_s / props_per_step),
             "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": ach_tflops / fp32_peak if fp32_peak else None,
             "ffma_tflops": f32.value, "ffma2_tflops": f32x2.value,
             "peak_source": "own FFMA / FFMA2 microbenchmark (qmc_diag_peaks2) on this GPU, max of the two; MEASURED_PEAKS.json has no FP32 peak",
             "algorithmic_flop_per_proposal": work["flop"],
-            "hbm": {"achieved": props_per_launch * work["window_bytes"] * (1 + accept_rate) / sweep_s * 1e-9,
+            "hbm": {"achieved": props_per_step * work["window_bytes"] * (1 + accept_rate) / sweep_s * 1e-9,
                     "peak": hbm_peak, "unit": "GB/s",
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "algorithmic_bytes_per_proposal": work["window_bytes"] * (1 + accept_rate)},
             "mufu_gops_peak": mufu.value,
-            "note": "bound is the FP32 FMA pipe of the CUDA cores (SURVEY.md section 8d: C <= 16 channels and fp32 "
-                    "parity rule out tensor cores; the per-proposal window is served from L2/HBM at ~0.14 of the HBM "
-                    "roofline, reported under 'hbm'); 'achieved' = algorithmic FLOP / sweep time",
+            "note": "'achieved' = algorithmic FLOP of the sweep / sweep time (live CUDA events); 'frac' is against the FP32 "
+                    "FMA peak of the CUDA cores, 'frac_of_bound' against whichever of FP32 / MUFU / HBM bounds one proposal "
+                    "(SURVEY.md section 8d).  Tensor cores: measured no-go for these 16-channel layers "
+                    "(profiles/r02_tc_layer_proto.txt)",
             "traffic": None,
         }
         roofline["sweep_kernel_launches_per_step"] = sweep_launches
-        roofline["proposals_per_launch"] = props_per_launch / max(sweep_launches, 1)
-        prof = os.path.join(ROOT, "profiles", "r01_sweep_traffic.json")
-        if os.path.exists(prof):
-            try:
-                roofline["traffic"] = json.load(open(prof))["dram_bytes_per_proposal"] * roofline["proposals_per_launch"]
-                roofline["traffic_source"] = "profiles/r01_sweep_traffic.json (ncu dram__bytes per proposal x proposals per launch)"
-            except Exception:
-                pass
+        roofline["proposals_per_launch"] = props_per_step / max(sweep_launches, 1)
+        # DRAM traffic is NOT measured by this run: it is the ncu figure of the committed profile x this run's launch size
+        for prof_name in ("r02_sweep_traffic.json", "r01_sweep_traffic.json"):
+            prof = os.path.join(ROOT, "profiles", prof_name)
+            if name in ("C3", "C5") and os.path.exists(prof):
+                try:
+                    roofline["traffic"] = json.load(open(prof))["dram_bytes_per_proposal"] * roofline["proposals_per_launch"]
+                    roofline["traffic_from_profile"] = ("profiles/%s: ncu dram__bytes_read+write per proposal of the C3 capture "
+                                                        "x proposals per launch of this run (not re-measured here)" % prof_name)
+                except Exception:
+                    pass
+                break
         line = {
             "metric": "metropolis_proposals_per_s", "value": value, "unit": "proposals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(name, dict(cfg, chains=S)), "chains_total": S * world,
-                       "l2": ("activation caches %.0f MB per GPU exceed the 126 MB L2 (inputs larger than L2); every "
-                              "step starts from a full forward that rewrites them" if cache_mb > 126 else
-                              "activation caches %.0f MB per GPU fit the L2 and are not flushed: parity-test "
-                              "configuration, not the headline workload") % cache_mb,
-                       "step": "mcmc_op + local energies + moment allreduce + gradient + gradient allreduce + Adam"},
+            "config": config_dict(name, cfg, S, world, args.sigma),
             "local_energies_per_s": float(S) * args.steps * world / (en_ms * 1e-3),
             "sweep_proposals_per_s": proposals / (sw_ms * 1e-3),
             "segments_ms_per_step": {"sweep": sw_ms / args.steps, "energy": en_ms / args.steps,
@@ -442,12 +439,14 @@ def run_cuda(args, cfg, name):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "proposals/s",
                     "h2d_bytes_per_step": S * n + params_host.numel() * 4,
-                    "d2h_bytes_per_step": S * n + S * 8, "steps": e2e_steps},
+                    "d2h_bytes_per_step": S * n + S * 8 + params_host.numel() * 4, "steps": e2e_steps,
+                    "step": "H2D parameters + lattices, OptimizeStep.run() (the timed step), D2H samples + energies + parameters"},
             "gpu_launches": gpu_launches,       # this library's kernels in the timed region (qmc_launch_count)
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg)
+            # bounded sample (~10-30 s) of the same workload on the host cores, same code path as --impl reference
+            line["cpu_baseline"] = CpuReference(cfg, args.sigma, args.ref_chains, args.ref_its, args.ref_energy).measure(1, 1)[3]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -466,6 +465,8 @@ def main():
     ap.add_argument("--ref-chains", type=int, default=256)
     ap.add_argument("--ref-its", type=int, default=256)
     ap.add_argument("--ref-energy", type=int, default=4)
+    ap.add_argument("--sigma", type=float, default=SCALE,
+                    help="std of the synthetic parameters (models.py SCALE = 1e-2: acceptance ~ 1; 1e-1: non-trivial)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

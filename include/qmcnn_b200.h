@@ -118,6 +118,13 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
                          int64_t n_sample_slots, uint8_t* accept_trace, float* logratio_trace,
                          unsigned long long* n_accept, void* stream);
 
+/* Fresh chains of Sampler.mcmc_reset (sampler.py:74-79: iid uniform +-1 lattices).  Stateless; spins
+ * [S, n] int8 on `device`.  Chain c gets a function of (seed, chain_id0 + c, reset_index) only -
+ * Philox-4x32-10 on counters the proposal stream never uses (oracle/philox.py: initial_spins) - so a
+ * chain's start does not depend on how the chains are sharded over ranks. */
+int qmc_init_spins(int device, int8_t* spins, int S, int n, uint64_t seed, int64_t chain_id0,
+                   int64_t reset_index, void* stream);
+
 /* Symmetry-averaged amplitude psi_sym(s) = (1/nsym) sum_g psi(s; W o g), g in D4
  * (symmetry.ipynb cell 0 defines the group; SURVEY.md section 8 the amplitude - the reference
  * has no amplitude code).  params_images [nsym, P]: the flat parameter vector of every image

@@ -10,6 +10,12 @@ defines its own stream and this file is its CPU twin:
     words r0..r3 = philox4x32_10(counter, key)
     flip position f (f < num_flips <= 3) = mulhi32(r_f, num_spins)
     uniform u in [0,1)                   = (r3 >> 8) * 2**-24
+
+Fresh initial lattices (``sampler.py:74-79`` draws them with ``tf.random_uniform``) come from the
+same generator on counters the proposal stream never uses (bit 31 of the second word set):
+
+    counter = (block, 0x80000000 | reset_index, chain_lo, chain_hi);  spin 128*block + 32*w + b
+    = +1 if bit b of word r_w is set else -1
 """
 import numpy as np
 
@@ -55,3 +61,19 @@ def sweep_randoms(seed, chain_ids, step0, n_steps, num_flips, num_spins):
     u = ((r[..., 3] >> np.uint32(8)).astype(np.float32)
          * np.float32(2.0 ** -24))
     return pos, u
+
+
+def initial_spins(seed, chain_ids, num_spins, reset_index=0):
+    """The +-1 lattices ``qmc_init_spins`` writes for the given global chains (int32 (S, num_spins)):
+    a function of (seed, global chain id, reset_index) only, so independent of how chains are sharded."""
+    chain_ids = np.asarray(chain_ids, dtype=np.uint64)
+    nblk = (num_spins + 127) // 128
+    ctr = np.zeros((chain_ids.size, nblk, 4), dtype=np.uint32)
+    ctr[..., 0] = np.arange(nblk, dtype=np.uint32)[None, :]
+    ctr[..., 1] = np.uint32(0x80000000 | (int(reset_index) & 0x7FFFFFFF))
+    ctr[..., 2] = (chain_ids & _MASK)[:, None]
+    ctr[..., 3] = (chain_ids >> np.uint64(32))[:, None]
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    r = philox4x32_10(ctr, key)                                       # (S, nblk, 4)
+    bits = (r[..., None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)   # (S, nblk, 4, 32)
+    return (bits.reshape(chain_ids.size, -1)[:, :num_spins].astype(np.int32) * 2 - 1)

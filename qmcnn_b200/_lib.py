@@ -66,6 +66,7 @@ SIGNATURES = {
     "qmc_logpsi_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "qmc_metropolis_sweep": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,
                                   _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "qmc_init_spins": (_i, [_i, _vp, _i, _i, _u64, _i64, _i64, _vp]),
     "qmc_set_image_params": (_i, [_vp, _i, _vp, _vp]),
     "qmc_sym_sweep_workspace_floats": (_sz, [_vp, _i, _i, _i]),
     "qmc_metropolis_sweep_sym": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,

@@ -61,7 +61,41 @@ static bool build_model(const qmc_model_desc* d, DevModel& m, std::string& err) 
     return true;
 }
 
+// fresh lattices: one Philox block = 128 spins (oracle/philox.py: initial_spins)
+__global__ void k_init_spins(int8_t* __restrict__ spins, int S, int n, unsigned long long seed, long long chain_id0,
+                             unsigned reset_word) {
+    const int nblk = (n + 127) / 128;
+    const long long total = (long long)S * nblk;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int chain = (int)(t / nblk), blk = (int)(t - (long long)chain * nblk);
+        const unsigned long long g = (unsigned long long)(chain_id0 + chain);
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, reset_word, (uint32_t)g, (uint32_t)(g >> 32)),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        int8_t* dst = spins + (size_t)chain * n + (size_t)blk * 128;
+        const int cnt = min(128, n - blk * 128);
+        for (int i = 0; i < cnt; ++i) dst[i] = ((w[i >> 5] >> (i & 31)) & 1u) ? 1 : -1;
+    }
+}
+
 extern "C" {
+
+int qmc_init_spins(int device, int8_t* spins, int S, int n, uint64_t seed, int64_t chain_id0, int64_t reset_index,
+                   void* stream) {
+    if (S < 0 || n < 1 || (S > 0 && !spins)) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "init_spins: bad argument");
+    if (S == 0) return QMC_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "bad device ordinal");
+    const long long total = (long long)S * ((n + 127) / 128);
+    const int blocks = (int)((total + 127) / 128 < 4096 ? (total + 127) / 128 : 4096);
+    ++g_launches;
+    k_init_spins<<<blocks, 128, 0, (cudaStream_t)stream>>>(spins, S, n, seed, chain_id0,
+                                                          0x80000000u | (uint32_t)(reset_index & 0x7FFFFFFF));
+    const cudaError_t e = cudaGetLastError();
+    if (prev != device) cudaSetDevice(prev);
+    return e == cudaSuccess ? QMC_OK : cuda_fail(nullptr, e, "init_spins");
+}
 
 const char* qmc_version(void) { return "qmcnn_b200 0.1 (sm_100a)"; }
 
@@ -107,12 +141,15 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     if (is) h->ip_sync = std::atoi(is);
     const char* ig = std::getenv("QMC_IP_GROUP");
     if (ig) h->ip_group = std::atoi(ig);
+    const char* icf = std::getenv("QMC_IP_CF");
+    if (icf) h->ip_cf = std::atoi(icf) != 0;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = ip_upload_tables(h);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(params)"); }
     if ((size_t)m.smem_param_floats * 4 > h->max_smem) {
@@ -131,6 +168,7 @@ int qmc_destroy(qmc_handle* h) {
     cudaFree(h->d_params);
     cudaFree(h->d_params_padded);
     cudaFree(h->d_sym_padded);
+    cudaFree(h->d_ip_tab);
     for (int i = 0; i < 2; ++i) {
         if (h->side_stream[i]) cudaStreamDestroy(h->side_stream[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
@@ -280,6 +318,7 @@ int qmc_set_image_params(qmc_handle* h, int nsym, const float* params_images, vo
         cudaError_t e = cudaSuccess;
         if (h->nsym != nsym) {
             cudaFree(h->d_sym_padded);
+    cudaFree(h->d_ip_tab);
             h->d_sym_padded = nullptr;
             e = cudaMalloc(&h->d_sym_padded, sizeof(float) * (size_t)nsym * h->m.smem_param_floats);
             h->nsym = e == cudaSuccess ? nsym : 0;

@@ -23,6 +23,8 @@ struct qmc_handle {
     int ip_group = 4;            // QMC_IP_GROUP: warps per phase group of k_sweep_ip<3>
     int ip_sync = 3;             // QMC_IP_SYNC: 0 = k_sweep_ip's warps run free, otherwise (default) a named barrier per
                                  // layer within each phase group of ip_group warps
+    bool ip_cf = true;           // conflict-free site tables for the in-place evaluator (QMC_IP_CF=0: the r01 order)
+    unsigned short* d_ip_tab = nullptr;   // device image of the tables (ip_upload_tables), or nullptr
     bool force_ip = false;       // QMC_SWEEP_PATH=inplace: use k_sweep_ip whenever the model is inside its coverage
     bool allow_batched = true;  // QMC_FORCE_PERSISTENT=1 disables the layer-synchronous batched path (energy + sweep)
     bool batched_sweep = false; // QMC_SWEEP_PATH=batched: use the batched path for the sweep too (default: persistent
@@ -171,6 +173,7 @@ LeanLaunch lean_launch_plan(const qmc_handle* h, int S);
 cudaError_t launch_sweep_lean(const qmc_handle* h, const SweepArgs& a, const LeanLaunch& ll, cudaStream_t st);
 struct IpLaunch { IpPlan ip; int warps, grid; size_t smem; bool ok; };
 IpPlan ip_plan(const qmc_handle* h);
+cudaError_t ip_upload_tables(qmc_handle* h);
 IpLaunch ip_launch_plan(const qmc_handle* h, int S);
 cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st);
 bool energy_ip_supported(const qmc_handle* h);

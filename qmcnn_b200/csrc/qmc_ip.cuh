@@ -92,11 +92,12 @@ __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip
 
 template <int K, int CIN, int COUT, int ACC, typename OutF, typename MidF>
 __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const float* wsm, const float* tin,
-                                                    int tw, int tarea, int side, int lane, OutF out, MidF mid) {
+                                                    int tw, int tarea, int side, int lane, OutF out, MidF mid,
+                                                    const unsigned short* tab) {
     const int npos = side * side;
     constexpr int PMAX = ACC / COUT;
     auto o = [&](int, int pos, int y, int x, int cog, float4 a) { out(pos, y, x, cog, a); };
-#define QMC_TILED(PP) conv_region_tiled<K, CIN, COUT, (PP), false, 1>(wbase, bbase, wsm, tin, 0, tw, tarea, side, side, lane, o, mid)
+#define QMC_TILED(PP) conv_region_tiled<K, CIN, COUT, (PP), false, 1>(wbase, bbase, wsm, tin, 0, tw, tarea, side, side, lane, o, mid, tab)
     if (PMAX == 1 || npos <= 32) return QMC_TILED(1);
     if (PMAX == 2 || npos <= 64) return QMC_TILED(2);
     if (PMAX == 3 || npos <= 96) return QMC_TILED(PMAX >= 3 ? 3 : 2);
@@ -150,7 +151,8 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                                                   const unsigned* mg, float* arena, float* spt, const int8_t* spins_s,
                                                   const float* __restrict__ cache, float* staging,
                                                   int site_f, int lane, int gid, int gthreads, float& dre,
-                                                  float* dim_out = nullptr) {
+                                                  float* dim_out = nullptr, const int* tabo = nullptr,
+                                                  const unsigned short* tab_s = nullptr) {
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n, D = m.D;
     const int T = ip.T, TA = ip.tarea, c = ip.c;
     const int y0 = site_f / Lx, x0 = site_f - y0 * Lx;
@@ -198,6 +200,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         side += 2 * p;
         const int rarea = side * side;
         const float* tin = arena + (size_t)((c - hn - p) * T + (c - hn - p)) * 4;
+        const unsigned short* tab = (tabo && tabo[l] >= 0) ? tab_s + tabo[l] : nullptr;   // conflict-free site deal
         auto sync = [] { __syncwarp(); };
         if (!last) {
             const float* plane = cache + L.act_off;
@@ -215,19 +218,19 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                 ip_gather_frame(arena4, ip, plane, ncg, n, hn, p, mg[l], y0, x0, Ly, Lx, lane);
             };
             if (L.cin == 16 && L.cout == 16)
-                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid);
+                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab);
             else
-                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid);
+                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab);
             stg += L.coutp * rarea;
             cp_async_wait_all();
         } else {
             auto out = [&](int pos, int, int, int cog, float4 a) { arena4[cog * rarea + pos] = a; };
             if (L.cin == 16 && L.cout == 16)
-                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync);
+                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
             else if (L.cin == 16 && L.cout == 8)
-                conv_region_pick_ip<3, 16, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync);
+                conv_region_pick_ip<3, 16, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
             else
-                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync);
+                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
         }
         __syncwarp();
     }

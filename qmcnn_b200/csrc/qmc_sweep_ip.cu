@@ -6,6 +6,7 @@
 // fewer than two warps to choose from).  Single-flip proposals of deep k = 3 models whose
 // windows fit one round of the register tile; everything else runs the classic kernel.
 #include <cstdlib>
+#include <vector>
 #include "qmc_host.h"
 #include "qmc_ip.cuh"
 
@@ -21,6 +22,26 @@ constexpr int kIpAcc = 64;            // accumulators per lane
 // is (4096 chains on 148 x 12 slots would otherwise be 2.3 waves = 77% efficiency).
 struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps; };
 
+// per-CTA words after the parameter block: division magics, site-table offsets, then the site tables (uint16)
+constexpr int kIpCtaWords = 2 * QMC_MAX_LAYERS;
+__host__ __device__ inline size_t ip_cta_bytes(const IpPlan& ip) { return (size_t)kIpCtaWords * 4 + (size_t)ip.tab_entries * 2; }
+
+// shared-memory images of the division magics, the table offsets and the site tables; returns the first per-warp byte
+__device__ __forceinline__ char* ip_cta_setup(float* after_params, const IpPlan& ip, const unsigned short* __restrict__ tab_g,
+                                              unsigned*& mg, int*& tabo, unsigned short*& tab_s) {
+    mg = reinterpret_cast<unsigned*>(after_params);
+    tabo = reinterpret_cast<int*>(mg + QMC_MAX_LAYERS);
+    tab_s = reinterpret_cast<unsigned short*>(mg + kIpCtaWords);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < QMC_MAX_LAYERS; ++j) { mg[j] = ip.mgW[j]; tabo[j] = tab_g ? ip.tab_off[j] : -1; }
+    }
+    if (tab_g)
+        for (int i = threadIdx.x; i < ip.tab_entries; i += blockDim.x) tab_s[i] = tab_g[i];
+    __syncthreads();
+    return reinterpret_cast<char*>(tab_s + ip.tab_entries);
+}
+
 // SYNC: 0 = warps run free; 1 = phase-group barrier per proposal only; 2 = CTA barrier per layer; 3 = per
 // layer among the four warps of a phase group (ip_barrier).  With barriers the warps of a group
 // stay in the same phase of the proposal, so the SM's instruction working set is a few loop
@@ -29,7 +50,8 @@ struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps; };
 // their chunk's end shadow a valid chain without writing anything, to keep barrier counts equal.
 template <int SYNC>
 __global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
-k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip, IpSlice sl) {
+k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip, IpSlice sl,
+           const unsigned short* __restrict__ tab_g) {
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
     load_params_to_smem(m, params, smem_f);
@@ -38,13 +60,8 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // division magics W_j = 2(j+2)p + 1 in shared memory: indexing the kernel-parameter array by layer would
     // make ptxas keep a local-memory copy, and those loads miss L1 (28 KB next to 220 KB of shared memory)
-    unsigned* mg = reinterpret_cast<unsigned*>(smem_f + m.smem_param_floats);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < QMC_MAX_LAYERS; ++j) mg[j] = ip.mgW[j];
-    }
-    __syncthreads();
-    char* wmem = reinterpret_cast<char*>(mg + QMC_MAX_LAYERS) + (size_t)warp * ip.per_warp_bytes;
+    unsigned* mg; int* tabo; unsigned short* tab_s;
+    char* wmem = ip_cta_setup(smem_f + m.smem_param_floats, ip, tab_g, mg, tabo, tab_s) + (size_t)warp * ip.per_warp_bytes;
     float* arena = reinterpret_cast<float*>(wmem);
     float* spt = arena + ip.arena_floats;
     int8_t* spins_s = reinterpret_cast<int8_t*>(spt + ip.spt_floats);
@@ -105,7 +122,8 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
             float dre;
             cp_async_wait_all();                              // (a rejected move's speculative commit copy)
             ip_barrier<SYNC>(gid, gthreads);
-            warp_eval_flip_ip<kIpAcc, SYNC>(m, ip, sp, mg, arena, spt, spins_s, cache, staging, f0, lane, gid, gthreads, dre);
+            warp_eval_flip_ip<kIpAcc, SYNC>(m, ip, sp, mg, arena, spt, spins_s, cache, staging, f0, lane, gid, gthreads, dre,
+                                            nullptr, tabo, tab_s);
             const float amp = expf(dre);                      // |exp(z)| = exp(Re z)
             const bool accept = __shfl_sync(0xffffffffu, (int)(amp * amp > u), 0) != 0;   // strict, sampler.py:125
             if (SYNC && !active) continue;                    // shadow: nothing is written
@@ -231,8 +249,63 @@ IpPlan ip_plan(const qmc_handle* h) {
     ip.mg2p = fastdiv_magic(2 * p);
     ip.mg2p1 = fastdiv_magic(2 * p + 1);
     for (int j = 0; j < m.D; ++j) ip.mgW[j] = fastdiv_magic(2 * (j + 2) * p + 1);
+    // site tables of the tiled layers (ip_site_table): P rows of 32 lanes each
+    int entries = 0;
+    for (int l = 0; l < QMC_MAX_LAYERS; ++l) ip.tab_off[l] = -1;
+    for (int l = 1; l < m.D; ++l) {
+        const int side = 1 + 2 * (l + 1) * p;
+        ip.tab_off[l] = entries;
+        entries += ip_sites_per_lane(kIpAcc, m.layer[l].cout, side * side) * kWarp;
+    }
+    ip.tab_entries = (entries + 7) & ~7;
     ip.ok = 1;
     return ip;
+}
+
+// Deal the side x side window of layer l to (site j, lane) slots so that the eight lanes of every quarter warp read
+// eight different 16-byte bank groups of the arena (pitch T float4): walk the sites in row-major order and give
+// each quarter the first unassigned sites whose (y * T + x) mod 8 it does not hold yet.  Row-major preference keeps
+// the staging stores of a quarter nearly contiguous.  Lanes >= G = ceil(npos / P) stay idle as before.
+static void ip_site_table(int side, int T, int P, unsigned short* tab) {
+    const int npos = side * side, G = (npos + P - 1) / P;
+    std::vector<char> taken(npos, 0);
+    for (int i = 0; i < P * kWarp; ++i) tab[i] = 0xFFFF;
+    int left = npos;
+    for (int j = 0; j < P; ++j)
+        for (int qd = 0; qd < 4; ++qd) {
+            unsigned used = 0;
+            for (int lane = qd * 8; lane < qd * 8 + 8 && lane < G && left > 0; ++lane) {
+                int pick = -1, fallback = -1;
+                for (int pos = 0; pos < npos; ++pos) {
+                    if (taken[pos]) continue;
+                    if (fallback < 0) fallback = pos;
+                    const int y = pos / side, x = pos - y * side;
+                    if (!((used >> ((y * T + x) & 7)) & 1u)) { pick = pos; break; }
+                }
+                if (pick < 0) pick = fallback;          // no conflict-free site is left for this quarter
+                const int y = pick / side, x = pick - y * side;
+                used |= 1u << ((y * T + x) & 7);
+                taken[pick] = 1;
+                --left;
+                tab[j * kWarp + lane] = (unsigned short)((y << 8) | x);
+            }
+        }
+}
+
+// device image of the site tables of a handle (built once, qmc_create)
+cudaError_t ip_upload_tables(qmc_handle* h) {
+    h->d_ip_tab = nullptr;
+    if (!h->ip_cf) return cudaSuccess;
+    const IpPlan ip = ip_plan(h);
+    if (!ip.ok || ip.tab_entries == 0) return cudaSuccess;
+    std::vector<unsigned short> tab(ip.tab_entries, 0xFFFF);
+    for (int l = 1; l < h->m.D; ++l) {
+        const int side = 1 + 2 * (l + 1) * h->m.p;
+        ip_site_table(side, ip.T, ip_sites_per_lane(kIpAcc, h->m.layer[l].cout, side * side), tab.data() + ip.tab_off[l]);
+    }
+    cudaError_t e = cudaMalloc(&h->d_ip_tab, tab.size() * sizeof(unsigned short));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(h->d_ip_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
 }
 
 IpLaunch ip_launch_plan(const qmc_handle* h, int S) {
@@ -241,7 +314,7 @@ IpLaunch ip_launch_plan(const qmc_handle* h, int S) {
     if (!h->allow_ip) return L;
     L.ip = ip_plan(h);
     if (!L.ip.ok) return L;
-    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + QMC_MAX_LAYERS * sizeof(unsigned);
+    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + ip_cta_bytes(L.ip);
     if (h->max_smem < cta_bytes + (size_t)L.ip.per_warp_bytes) return L;
     int w = (int)((h->max_smem - cta_bytes) / (size_t)L.ip.per_warp_bytes);
     if (w > kIpMaxWarps) w = kIpMaxWarps;
@@ -287,7 +360,7 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
         const long long left = sl.n_tasks - sl.task0;
         const long long ctas = ((left < slots ? left : slots) + L.warps - 1) / L.warps;
         ++g_launches;
-        kern<<<(int)ctas, L.warps * 32, L.smem, st>>>(h->m, h->d_params, a, L.ip, sl);
+        kern<<<(int)ctas, L.warps * 32, L.smem, st>>>(h->m, h->d_params, a, L.ip, sl, h->d_ip_tab);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -304,20 +377,15 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
 __global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
 k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
             const float* __restrict__ cache_all, float2* __restrict__ partial, int nchunks, IpPlan ip,
-            int group_warps) {
+            int group_warps, const unsigned short* __restrict__ tab_g) {
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
     load_params_to_smem(m, params, smem_f);
     const float* sp = smem_f;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    unsigned* mg = reinterpret_cast<unsigned*>(smem_f + m.smem_param_floats);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int j = 0; j < QMC_MAX_LAYERS; ++j) mg[j] = ip.mgW[j];
-    }
-    __syncthreads();
-    char* wmem = reinterpret_cast<char*>(mg + QMC_MAX_LAYERS) + (size_t)warp * ip.per_warp_bytes;
+    unsigned* mg; int* tabo; unsigned short* tab_s;
+    char* wmem = ip_cta_setup(smem_f + m.smem_param_floats, ip, tab_g, mg, tabo, tab_s) + (size_t)warp * ip.per_warp_bytes;
     float* arena = reinterpret_cast<float*>(wmem);
     float* spt = arena + ip.arena_floats;
     int8_t* spins_s = reinterpret_cast<int8_t*>(spt + ip.spt_floats);
@@ -347,7 +415,7 @@ k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restri
             float dre, dim, sn, cn;
             ip_barrier<3>(gid, gthreads);
             warp_eval_flip_ip<kIpAcc, 3, false>(m, ip, sp, mg, arena, spt, spins_s, cache, nullptr, i, lane, gid,
-                                                gthreads, dre, &dim);
+                                                gthreads, dre, &dim, tabo, tab_s);
             if (!active) continue;
             const float amp = expf(dre);
             sincosf(dim, &sn, &cn);
@@ -363,14 +431,14 @@ bool energy_ip_supported(const qmc_handle* h) {
     if (!h->allow_ip) return false;
     const IpPlan ip = ip_plan(h);
     if (!ip.ok) return false;
-    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + QMC_MAX_LAYERS * sizeof(unsigned);
+    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + ip_cta_bytes(ip);
     return h->max_smem >= cta_bytes + (size_t)ip.per_warp_bytes;
 }
 
 cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, const float* cache, float2* partial,
                              int nchunks, cudaStream_t st) {
     const IpPlan ip = ip_plan(h);
-    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + QMC_MAX_LAYERS * sizeof(unsigned);
+    const size_t cta_bytes = (size_t)h->m.smem_param_floats * 4 + ip_cta_bytes(ip);
     int w = (int)((h->max_smem - cta_bytes) / (size_t)ip.per_warp_bytes);
     if (w > kIpMaxWarps) w = kIpMaxWarps;
     if (h->max_warps_override > 0 && w > h->max_warps_override) w = h->max_warps_override;
@@ -383,7 +451,7 @@ cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, co
     if (e != cudaSuccess) return e;
     ++g_launches;
     k_energy_ip<<<grid, w * 32, smem, st>>>(h->m, h->d_params, spins, N, cache, partial, nchunks, ip,
-                                            h->ip_group > 0 ? h->ip_group : 4);
+                                            h->ip_group > 0 ? h->ip_group : 4, h->d_ip_tab);
     return cudaGetLastError();
 }
 

@@ -167,11 +167,38 @@ class AdamTF1(object):
         self.flat.addcdiv_(self.m, self.v.sqrt().add_(self.eps), value=-lr_t)
 
 
+def _event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+class EnergiesOp(object):
+    """First element of what ``optimize_op`` returns (``mcmc_tf.py:157-179`` returns
+    ``(energies, train_op)``): the local energies of the samples the most recent
+    ``train_op.run()`` drew.  ``eval()`` / ``numpy()`` fetch them."""
+
+    def __init__(self, step):
+        self._step = step
+
+    def eval(self):
+        if self._step.last_energies is None:
+            raise _lib.QmcError("energies: run the train_op first (sess.run(optimize) runs both together)")
+        return self._step.last_energies
+
+    def numpy(self):
+        return self.eval().cpu().numpy()
+
+
 class OptimizeStep(object):
-    """What ``optimize_op`` returns: ``run()`` does one VMC iteration
-    (``mcmc_tf.py:156-179``): sample, local energies, gradient of ``loss_op``, Adam.
-    Under ``torch.distributed`` (one rank per GPU, chains sharded) the energy
-    moments and the gradient are all-reduced over NCCL - the only collectives."""
+    """What ``optimize_op`` returns.  It unpacks like the reference's return value,
+
+        energies, train_op = optimize_op(sampler, model, energy_fn)        # mcmc_tf.py:157-179
+
+    and ``run()`` is the eager stand-in for ``sess.run(optimize, feed_dict={sampler.new_samples: ...})``
+    (``mcmc_tf.py:218-222``): one VMC iteration - sample, local energies, gradient of ``loss_op``,
+    TF-1 Adam - returning the sampled local energies.  Under ``torch.distributed`` (one rank per GPU,
+    chains sharded) the energy moments and the gradient are all-reduced over NCCL - the only collectives."""
 
     def __init__(self, sampler, model, energy_fn, learning_rate=LEARNING_RATE, group=None):
         self.sampler, self.model, self.energy_fn = sampler, model, energy_fn
@@ -179,28 +206,61 @@ class OptimizeStep(object):
         self.group = group
         self.last_grad = None
         self.last_energy = None
+        self.last_energies = None
+        self.energies = EnergiesOp(self)
+        self.record_events = False      # bench.py: CUDA events at the phase boundaries of run() -> last_events
+        self.last_events = None
+
+    # (energies, train_op) like the reference
+    def __iter__(self):
+        return iter((self.energies, self))
+
+    def __len__(self):
+        return 2
+
+    def __getitem__(self, i):
+        return (self.energies, self)[i]
 
     def run(self, new_samples=None):
         from . import distributed as D
         if new_samples is not None:
             self.sampler.new_samples = bool(new_samples)
+        ev = []
+        mark = (lambda: ev.append(_event())) if self.record_events else (lambda: None)
+        mark()
         self.sampler.mcmc_op()
+        mark()
         samples = self.sampler.samples_int8()
         energies = self.energy_fn(samples)
         n_tot, e_mean, _, stderr = D.allreduce_energy_moments(energies, self.group)   # collective 1
+        mark()
         self.last_energy = (e_mean, stderr)
         weights = D.vmc_weights(energies, e_mean, n_tot)
         grad = logpsi_gradient(self.model, samples, weights, self.sampler.system_shape)
         D.allreduce_gradient(grad, self.group)                                        # collective 2
         self.last_grad = grad
         self.optimizer.step(grad)
+        mark()
+        self.last_events = ev or None       # [start, after sweep, after energies + allreduce, after gradient + Adam]
+        self.last_energies = energies
         return energies
+
+
+def run(fetches, feed_dict=None):
+    """Eager stand-in for ``sess.run`` on what ``optimize_op`` / ``eval_op`` return:
+    ``e, _ = run(optimize, feed_dict={"new_samples": it == 0})`` (``mcmc_tf.py:220-222``)."""
+    new_samples = None if not feed_dict else feed_dict.get("new_samples")
+    if isinstance(fetches, OptimizeStep):
+        return fetches.run(new_samples=new_samples), None
+    if callable(fetches):
+        return fetches()
+    raise _lib.QmcError("run: expected the result of optimize_op or a callable")
 
 
 @scope_op()
 def optimize_op(sampler, model, energy_fn, learning_rate=LEARNING_RATE, group=None):
-    """``mcmc_tf.py:156-179``. Returns an :class:`OptimizeStep`; ``.run()`` returns the
-    sampled local energies after applying one Adam update."""
+    """``mcmc_tf.py:156-179``: returns ``(energies, train_op)`` - an :class:`OptimizeStep` that unpacks
+    into the two; ``train_op.run()`` applies one Adam update and returns the sampled local energies."""
     return OptimizeStep(sampler, model, energy_fn, learning_rate, group)
 
 

@@ -112,40 +112,39 @@ class _Model(object):
         return factors, logpsi, cache
 
     @scope_op("factors")
-    def factors(self, x, check_periodic=True):
-        """``models.py:31-67`` / ``95-131``.
+    def factors(self, x, periodic=False):
+        """``models.py:31-67`` / ``95-131``: the reference's ``factors`` is a plain VALID
+        cross-correlation stack, so it accepts ANY +-1 array at least ``r`` wide and returns
+        complex64 ``(N,) + (shape - r + 1)`` - e.g. the ``(2K-1)^d`` windows of ``mcmc_tf.py:81-84``
+        give ``K^d`` factors.
 
-        x : (N,) + padded lattice, +-1, wrap-padded by (r-1)//2 as the reference's
-        callers do.  Returns complex64 (N,) + system_shape.  The CUDA path
-        evaluates the periodic lattice directly, so ``x`` must be a periodic
-        image (checked unless ``check_periodic=False``).
+        The CUDA kernels evaluate periodic lattices.  A VALID output at centre c only reads the
+        input inside c +- (r-1)/2, so the VALID result of ``x`` is the interior of the periodic
+        factors of ``x`` itself taken as a lattice: that is what runs here (no host sync, no
+        assumption about ``x``).  ``periodic=True``: the caller guarantees that ``x`` is a lattice
+        wrap-padded by (r-1)//2 (what ``pad`` produces, ``sampler.py:85-88``); only the inner lattice
+        is evaluated then - the same numbers for (1 + (r-1)/L)^d less work.  Nothing is checked.
         """
         x = torch.as_tensor(x, device=self.device)
         halo = self._halo()
-        shape = tuple(int(s) - 2 * halo for s in x.shape[1:])
-        if len(shape) != self.n_dims or min(shape) < 1:
-            raise _lib.QmcError("factors: expected (N,) + (L+r-1,)*n_dims wrap-padded input")
+        if x.dim() != self.n_dims + 1:
+            raise _lib.QmcError("factors: expected (N,) + a %d-dimensional +-1 array" % self.n_dims)
+        full = tuple(int(s) for s in x.shape[1:])
+        inner = tuple(s - 2 * halo for s in full)
+        if min(inner) < 1:
+            raise _lib.QmcError("factors: the input must be at least r = %d wide along every axis" % self.r)
+        core = (slice(None),) + tuple(slice(halo, halo + s) for s in inner)
+        if periodic:
+            lattice, shape, out_sl = x[core], inner, None
+        else:
+            lattice, shape, out_sl = x, full, core
+        flat = lattice.reshape(x.shape[0], -1)
         if self.n_dims != 2:
-            sl = (slice(None),) + tuple(slice(halo, halo + s) for s in shape)
-            inner = x[sl]
-            if check_periodic and halo:
-                img = inner
-                for ax, s in enumerate(shape):
-                    idx = torch.arange(-halo, s + halo, device=x.device) % s
-                    img = img.index_select(ax + 1, idx)
-                if not torch.equal(img, x):
-                    raise _lib.QmcError("factors: input is not a periodic (wrap-padded) image")
-            f, _ = self.nd_forward(inner.reshape(x.shape[0], -1), shape)
-            return f.view((x.shape[0],) + shape)
-        inner = x[:, halo:halo + shape[0], halo:halo + shape[1]]
-        if check_periodic and halo:
-            iy = torch.arange(-halo, shape[0] + halo, device=x.device) % shape[0]
-            ix = torch.arange(-halo, shape[1] + halo, device=x.device) % shape[1]
-            if not torch.equal(inner[:, iy][:, :, ix], x):
-                raise _lib.QmcError("factors: input is not a periodic (wrap-padded) image; the CUDA "
-                                    "path evaluates periodic lattices only")
-        f, _, _ = self.forward_unpadded(inner.reshape(x.shape[0], -1), shape)
-        return f.view((x.shape[0],) + shape)
+            f, _ = self.nd_forward(flat, shape)
+        else:
+            f, _, _ = self.forward_unpadded(flat, shape)
+        f = f.view((x.shape[0],) + shape)
+        return f if out_sl is None else f[out_sl].contiguous()
 
     def log_psi(self, spins, system_shape):
         """log psi of UN-padded states (N, Ly*Lx) -> complex64 (N,)."""

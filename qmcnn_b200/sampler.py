@@ -53,6 +53,14 @@ class Sampler(object):
         self.device = model.device
         S, n = self.num_samplers, self.num_spins
         self._nd = getattr(model, "n_dims", 2) != 2       # 1-D / 3-D lattices: the generic path (qmc_nd_sweep)
+        from .symmetry import SymmetrizedModel
+        if not self._nd and not isinstance(model, SymmetrizedModel):
+            # Outside the incremental kernels' coverage (flip bounding box + receptive field wider than the
+            # lattice: two independent flip sites of a deep model, sampler.py:106-122) the chain runs the
+            # reference's own algorithm - one full network evaluation per proposal - on the generic path.
+            h = model.handle(self.system_shape)
+            if _lib.load().qmc_sweep_workspace_floats(h.ptr, S, num_flips) == 0:
+                self._nd = True
         if self._nd:
             self._sym = False
             self._desc = model.nd_desc(self.system_shape)
@@ -63,13 +71,11 @@ class Sampler(object):
             self._n_accept = torch.zeros(1, dtype=torch.int64, device=self.device)
             self.flip_positions_var = self.accept_sample_var = self._initial_states = None
             self._step_base = 0
-            self._gen = torch.Generator(device=self.device)
-            self._gen.manual_seed(self.seed + 7919 * (self.chain_id0 + 1))
+            self._resets = 0
             self.accept_trace = self.logratio_trace = None
             return
         self._h = model.handle(self.system_shape)
         lib = _lib.load()
-        from .symmetry import SymmetrizedModel
         self._sym = isinstance(model, SymmetrizedModel)
         nimg = model.NSYM if self._sym else 1
         self._spins = torch.zeros((S, n), dtype=torch.int8, device=self.device)
@@ -89,8 +95,7 @@ class Sampler(object):
         self.accept_sample_var = None       # fed-in uniforms                - sampler.py:65-69
         self._initial_states = None
         self._step_base = 0                 # Philox step offset: a fresh stream per mcmc_op call
-        self._gen = torch.Generator(device=self.device)
-        self._gen.manual_seed(self.seed + 7919 * (self.chain_id0 + 1))
+        self._resets = 0                    # fresh-lattice draws so far (keys the initial-state stream)
         self.accept_trace = None
         self.logratio_trace = None
 
@@ -132,10 +137,16 @@ class Sampler(object):
         if (flip_positions is None) != (accept_sample is None):
             raise _lib.QmcError("feed: give both flip_positions and accept_sample or neither")
         if flip_positions is not None:
-            self.flip_positions_var = torch.as_tensor(flip_positions, device=self.device) \
+            fp = torch.as_tensor(flip_positions, device=self.device) \
                 .to(torch.int32).reshape(-1, self.num_samplers, self.num_flips).contiguous()
-            self.accept_sample_var = torch.as_tensor(accept_sample, device=self.device) \
+            ua = torch.as_tensor(accept_sample, device=self.device) \
                 .to(torch.float32).reshape(-1, self.num_samplers).contiguous()
+            # the kernels index shared and global memory with these sites: refuse anything off the lattice
+            if fp.shape[0] != ua.shape[0]:
+                raise _lib.QmcError("feed: flip_positions cover %d steps, accept_sample %d" % (fp.shape[0], ua.shape[0]))
+            if fp.numel() and (int(fp.min()) < 0 or int(fp.max()) >= self.num_spins):
+                raise _lib.QmcError("feed: flip_positions must lie in [0, %d)" % self.num_spins)
+            self.flip_positions_var, self.accept_sample_var = fp, ua
 
     # ---- reference ops -------------------------------------------------------------
     @scope_op()
@@ -146,8 +157,15 @@ class Sampler(object):
             if self._initial_states is not None:
                 self._spins.copy_(self._initial_states)
             else:
-                self._spins.copy_(torch.randint(0, 2, self._spins.shape, generator=self._gen,
-                                                device=self.device, dtype=torch.int8) * 2 - 1)
+                # iid +-1 (sampler.py:74-75), keyed by (seed, GLOBAL chain id, reset count): a chain's start does
+                # not depend on how the chains are sharded over ranks
+                rc = _lib.load().qmc_init_spins(self.device.index or 0, self._spins.data_ptr(), self.num_samplers,
+                                                self.num_spins, self.seed, self.chain_id0, self._resets,
+                                                _stream_ptr(self.device))
+                if rc != 0:
+                    raise _lib.QmcError("qmc_init_spins failed (%d): %s"
+                                        % (rc, (_lib.load().qmc_last_error(None) or b"?").decode()))
+                self._resets += 1
         if self._nd:
             self._factors = self.model.nd_forward(self._spins, self.system_shape)[0]      # sampler.py:85-88
             self._samples.zero_()
@@ -248,7 +266,7 @@ class Sampler(object):
         n_its = self.sample_its if n_its is None else int(n_its)
         self._sweep(0, n_its, trace)
         if self.flip_positions_var is None:
-            self._step_base += self.sample_its
+            self._step_base += max(n_its, self.sample_its)      # never reuse a part of the Philox stream
         return self._samples.view(self.num_samples, self.num_spins).to(torch.int32)
 
     def samples_int8(self):

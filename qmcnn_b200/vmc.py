@@ -38,6 +38,22 @@ NUM_EVAL_SAMPLES = 1000
 EVAL_FREQ = 20
 
 
+def make_samplers(model, system_shape, num_samples, num_eval_samples, num_flips, seed=0, group=None,
+                  sampler_cls=Sampler):
+    """The two samplers of ``mcmc_tf.py:208-209``.  Data parallelism: ``num_samples`` / ``num_eval_samples`` are
+    PER RANK and rank g owns the global chains [g * num_samplers, (g + 1) * num_samplers).  Initial lattices and
+    proposals are Philox streams keyed by the global chain id, so the ranks draw different chains and the
+    all-reduced batch really is world_size times larger (and equals a single-rank run of all the chains)."""
+    from . import distributed as D
+    rank, _ = D.world(group)
+    chains = lambda n: min(n, sampler_cls.MAX_NUM_SAMPLERS)
+    sampler = sampler_cls(model, system_shape, model.r, num_samples, num_flips, seed=seed,
+                          chain_id0=rank * chains(num_samples))
+    eval_sampler = sampler_cls(model, system_shape, model.r, num_eval_samples, num_flips, seed=seed + 1,
+                               chain_id0=rank * chains(num_eval_samples))
+    return sampler, eval_sampler
+
+
 def run_vmc(model, system_shape, hamiltonian="heisenberg", h=H, num_samples=NUM_SAMPLES,
             num_eval_samples=NUM_EVAL_SAMPLES, optimization_its=OPTIMIZATION_ITS, eval_freq=EVAL_FREQ,
             learning_rate=LEARNING_RATE, energy_batch_size=ENERGY_BATCH_SIZE, seed=0, group=None,
@@ -53,8 +69,8 @@ def run_vmc(model, system_shape, hamiltonian="heisenberg", h=H, num_samples=NUM_
         num_flips = 2
     else:
         raise ValueError("hamiltonian must be 'tfim' or 'heisenberg'")
-    sampler = sampler_cls(model, system_shape, model.r, num_samples, num_flips, seed=seed)              # :208
-    eval_sampler = sampler_cls(model, system_shape, model.r, num_eval_samples, num_flips, seed=seed + 1)  # :209
+    sampler, eval_sampler = make_samplers(model, system_shape, num_samples, num_eval_samples, num_flips, seed,
+                                          group, sampler_cls)                                           # :208-209
     optimize = optimize_op(sampler, model, energy_fn, learning_rate=learning_rate, group=group)         # :211
     history = []
     for it in range(optimization_its):                                                      # :218

@@ -116,3 +116,57 @@ def test_philox_streams_do_not_depend_on_the_partition():
             first = r * base + min(r, rem)
             p, u = sweep_randoms(77, first + np.arange(cnt), 0, steps, 1, 400)
             assert np.array_equal(p, pos_all[:, first:first + cnt]) and np.array_equal(u, u_all[:, first:first + cnt])
+
+
+def test_initial_lattices_do_not_depend_on_the_partition():
+    """Fresh chains (sampler.py:74-79) are keyed by (seed, global chain id, reset count) like the proposals."""
+    from oracle.philox import initial_spins
+    total, n = 24, 400
+    full = initial_spins(77, np.arange(total), n)
+    assert full.shape == (total, n) and set(np.unique(full)) == {-1, 1}
+    assert abs(full.mean()) < 0.05 and len({r.tobytes() for r in full}) == total
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            first, cnt = (r * (total // world) + min(r, total % world), total // world + (1 if r < total % world else 0))
+            parts.append(initial_spins(77, first + np.arange(cnt), n))
+        assert np.array_equal(np.concatenate(parts), full)
+    assert not np.array_equal(initial_spins(77, np.arange(total), n, reset_index=1), full)
+    assert not np.array_equal(initial_spins(78, np.arange(total), n), full)
+
+
+class _RecordingSampler(object):
+    MAX_NUM_SAMPLERS = 1000
+
+    def __init__(self, model, system_shape, r, num_samples, num_flips, seed=0, chain_id0=0):
+        self.args = dict(num_samples=num_samples, num_flips=num_flips, seed=seed, chain_id0=chain_id0)
+
+
+def _vmc_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from qmcnn_b200 import vmc
+
+        class M(object):
+            r = 5
+        a, b = vmc.make_samplers(M(), (6, 6), 64, 2500, 2, seed=9, sampler_cls=_RecordingSampler)
+        out[rank] = (a.args, b.args)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_run_vmc_gives_every_rank_its_own_chains():
+    """ADVICE r01: under torchrun every rank must own different global chains (chain_id0 = rank * num_samplers);
+    identical ids would make the all-reduced batch world_size copies of the same samples."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_vmc_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0][0]["chain_id0"] == 0 and out[1][0]["chain_id0"] == 64
+    assert out[0][1]["chain_id0"] == 0 and out[1][1]["chain_id0"] == 1000     # capped at MAX_NUM_SAMPLERS chains
+    assert out[0][0]["seed"] == out[1][0]["seed"] == 9 and out[0][1]["seed"] == 10

@@ -159,6 +159,34 @@ def test_helpers_match_reference():
             assert np.array_equal(got, g[tag + "/update_windows"]), tag
 
 
+def test_product_helper_shims_match_reference():
+    """The PRODUCT's helper API (qmcnn_b200.helpers: create_index_matrix, all_windows, interactions, pad / unpad,
+    gather_windows, update_windows - eager torch, any device) against the same reference-run vectors."""
+    import torch
+    import qmcnn_b200.helpers as ph
+    g = np.load(os.path.join(GOLD, "helpers.npz"))
+    specs = {"1d": ((7,), (3,)), "2d": ((4, 5), (3, 3)), "2d_even": ((6, 6), (4, 4)),
+             "3d": ((3, 4, 3), (3, 3, 3)), "2d_wrap": ((3, 3), (5, 5))}
+    t = lambda a: torch.as_tensor(np.asarray(a))
+    for tag, (shape, win) in specs.items():
+        x, s = g[tag + "/x"], g[tag + "/s"]
+        im = ph.create_index_matrix(shape, win)
+        assert im.dtype == np.int32 and np.array_equal(im, g[tag + "/index_matrix"]), tag
+        assert np.array_equal(ph.all_windows(t(x), shape, win).numpy(), g[tag + "/all_windows"]), tag
+        assert np.array_equal(ph.interactions(t(s), shape).numpy(), g[tag + "/interactions"]), tag
+        p = tuple(int(v) for v in g[tag + "/pad_size"])
+        padded = ph.pad(t(x).reshape((3,) + shape), shape, p)
+        assert np.array_equal(padded.numpy(), g[tag + "/padded"]), tag
+        assert np.array_equal(ph.unpad(padded, p).numpy(), g[tag + "/unpadded"]), tag
+        if tag + "/centers" in g:
+            assert np.array_equal(ph.gather_windows(t(x), t(g[tag + "/centers"]), shape, win).numpy(),
+                                  g[tag + "/gather_windows"]), tag
+        if tag + "/update_windows" in g:
+            got = ph.update_windows(t(x).clone(), t(g[tag + "/centers"]), t(g[tag + "/updates"]),
+                                    t(g[tag + "/mask"]), shape, win)
+            assert np.array_equal(got.numpy(), g[tag + "/update_windows"]), tag
+
+
 def test_factors_in_1d_2d_3d():
     """models.py:56-61 / 118-123: the conv1d / conv2d / conv3d branches."""
     g = np.load(os.path.join(GOLD, "factors_nd.npz"))

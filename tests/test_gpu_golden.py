@@ -47,7 +47,7 @@ def energy(case, model, states):
     return q.heisenberg_energy(model, states, system_shape=case["shape"])
 
 
-SWEEPABLE = [n for n in sorted(CASES) if n != "heis_dcrbm"]
+SWEEPABLE = sorted(CASES)       # incl. heis_dcrbm: two flips of a deep model run the generic full-forward path
 
 
 @pytest.fixture(params=["default", "inplace", "pingpong", "batched"])
@@ -85,13 +85,14 @@ def test_mcmc_op_reproduces_reference_chain(name, sweep_path):
     assert np.abs(lr[ok] - g["logratio_re"][ok]).max() <= 2e-5 * max(1.0, np.abs(g["logratio_re"][ok]).max())
 
 
-def test_two_flip_deep_model_gap_is_loud():
-    """Known gap: pair flips of a deep model whose flip box plus receptive
-    field exceeds the lattice are refused with an error, never computed differently."""
+def test_two_flip_deep_model_uses_the_generic_path():
+    """sampler.py:106-122 samples any model with num_flips = 2.  Two independent uniform sites of a deep model
+    have a bounding box + receptive field wider than the lattice, which the incremental kernels do not cover:
+    the Sampler then runs the generic full-forward path (the reference's own algorithm) instead of raising."""
     case, g = CASES["heis_dcrbm"], load("heis_dcrbm")
     model = build(case["model"], g)
-    with pytest.raises(q.QmcError):
-        make_sampler(case, model)
+    smp = make_sampler(case, model)
+    assert smp._nd, "expected the generic path for a two-flip DCRBM on 6x6"
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -149,3 +150,24 @@ def test_two_optimisation_iterations(name):
         opt.step(torch.as_tensor(gref, device="cuda"))
         want_p = np.concatenate([g["f32/" + pre + "param/" + n].ravel() for n in model.names])
         assert np.abs(opt.flat.cpu().numpy() - want_p).max() <= 2e-6
+
+
+def test_eval_op_and_optimize_op_return_shapes():
+    """mcmc_tf.py:182-194 eval_op = batched energies of a fresh mcmc_op; mcmc_tf.py:157-179 optimize_op returns
+    (energies, train_op) - the product's object unpacks into the two and `run` is the eager sess.run."""
+    name = "c1_tfim_crbm"
+    case, g = CASES[name], load(name)
+    model = build(case["model"], g)
+    smp = make_sampler(case, model)
+    smp.feed(g["initial_states"], g["flip_positions"].astype(np.int32), g["accept_sample"])
+    fn = lambda s: energy(case, model, s)
+    e = q.eval_op(smp, model, fn, batch_size=case["num_samples"] // 2).cpu().numpy()
+    assert np.array_equal(smp.samples_int8().cpu().numpy(), g["samples"])
+    assert np.abs(e - g["energies"]).max() <= 1e-5 * np.abs(g["energies"]).max()
+    opt = q.optimize_op(smp, model, fn)
+    energies, train_op = opt
+    assert len(opt) == 2 and train_op is opt and opt[0] is energies
+    with pytest.raises(q.QmcError):
+        energies.eval()
+    e2, _ = q.mcmc.run(opt, feed_dict={"new_samples": True})
+    assert torch.equal(energies.eval(), e2) and e2.shape == (case["num_samples"],)

@@ -76,6 +76,8 @@ def test_forward_matches_oracle(name, kind, shape, kw, scale):
     want64 = om.astype(np.float64).factors(xp)
     got = gm.factors(torch.as_tensor(xp)).cpu().numpy()
     assert got.shape == want32.shape and got.dtype == np.complex64
+    got_p = gm.factors(torch.as_tensor(xp), periodic=True).cpu().numpy()
+    assert np.abs(got_p - got).max() < 2e-6 * max(1.0, np.abs(want64).max())
     # per-site factors: absolute error at the fp32 rounding level of the values
     assert np.abs(got - want64).max() < 2e-6 * max(1.0, np.abs(want64).max())
     lp = gm.log_psi(torch.as_tensor(s), shape).cpu().numpy()
@@ -84,13 +86,22 @@ def test_forward_matches_oracle(name, kind, shape, kw, scale):
     assert rel_err(lp, want32.reshape(7, -1).sum(1)) < LOGPSI_RTOL
 
 
-def test_forward_rejects_non_periodic_input():
+@pytest.mark.parametrize("kind,kw", [("crbm", dict(k=5, alpha=4)), ("dcrbm", dict(k=3, layers=[8, 8, 8]))])
+def test_factors_on_non_periodic_windows(kind, kw):
+    """models.py:31-67 / 95-131 are VALID convolutions: `factors` must answer on ANY array at least r wide, e.g.
+    the (2K-1)^2 windows of mcmc_tf.py:81-84 (K^2 factors each) or a rectangular, non-periodic patch."""
     from gpu_util import make_pair
-    gm, om = make_pair("crbm", 6, 1e-2, 1, k=3, alpha=2)
-    x = torch.ones((2, 8, 8), dtype=torch.int32)
-    x[0, 0, 0] = -1
+    gm, om = make_pair(kind, 12, 1e-1, 3, **kw)
+    rng = np.random.default_rng(9)
+    r = om.r
+    for shape in ((2 * r - 1, 2 * r - 1), (r, r + 3), (r + 6, r + 1)):
+        x = (rng.integers(0, 2, (5,) + shape) * 2 - 1).astype(np.int32)
+        want = om.astype(np.float64).factors(x)
+        got = gm.factors(torch.as_tensor(x)).cpu().numpy()
+        assert got.shape == want.shape == (5, shape[0] - r + 1, shape[1] - r + 1)
+        assert np.abs(got - want).max() < 2e-6 * max(1.0, np.abs(want).max())
     with pytest.raises(_q().QmcError):
-        gm.factors(x)
+        gm.factors(torch.ones((2, r - 1, r + 2), dtype=torch.int32))
 
 
 def test_forward_empty_and_single():
@@ -251,6 +262,45 @@ def test_sweep_lockstep_two_flips_crbm():
     gs, os_, ties, err_gpu, err_f32, acc = _lockstep(gm, om, (10, 10), 32, 200, 2, seed=13)
     assert acc[1, 0]                       # identity proposal always accepted
     _check_lockstep(ties, err_gpu, err_f32)
+
+
+def test_sweep_lockstep_two_flips_deep_model_10x10():
+    """a Heisenberg VMC with DCRBM [8,8,8] on the default 10x10 lattice (flip box up to 6 wide + r - 1 = 6
+    > 10) must sample: generic full-forward path, stepped against the float64 oracle."""
+    from gpu_util import make_pair
+    gm, om = make_pair("dcrbm", 10, 2e-1, 107, layers=[8, 8, 8])
+    gs, os_, ties, err_gpu, err_f32, acc = _lockstep(gm, om, (10, 10), 16, 120, 2, seed=24, name="heis-dcrbm888-10x10")
+    assert gs._nd
+    assert acc[1, 0]                       # identity proposal always accepted
+    _check_lockstep(ties, err_gpu, err_f32)
+    e = _q().heisenberg_energy(gm, gs.spins, system_shape=(10, 10)).cpu().numpy()
+    want = oracle.heisenberg_energy(om.astype(np.float64), gs.spins.cpu().numpy().astype(np.int32), (10, 10), om.r)
+    assert np.abs(e - want).max() <= ELOC_RTOL * np.abs(want).max()
+
+
+def test_chain_shards_union_equals_single_run():
+    """Data parallelism by chains: two samplers owning global chains [0, S) and [S, 2S) produce exactly the rows a
+    single sampler of 2S chains produces - initial lattices (qmc_init_spins == oracle.philox.initial_spins) and
+    proposals are functions of (seed, global chain id, step) only."""
+    from gpu_util import make_pair
+    from oracle.philox import initial_spins
+    q = _q()
+    gm, om = make_pair("dcrbm", 8, 2e-1, 17, layers=[8, 8])
+    S = 12
+    GS = type("GS", (q.Sampler,), dict(SWEEPFACTOR=1, THERMFACTOR=1))
+    probe = GS(gm, (8, 8), 5, 2 * S, 1, seed=31, chain_id0=0)
+    probe.mcmc_reset()
+    assert np.array_equal(probe.spins.cpu().numpy().astype(np.int32), initial_spins(31, np.arange(2 * S), 64))
+    probe.mcmc_reset()                   # a second fresh draw is a new stream (reset count 1)
+    assert np.array_equal(probe.spins.cpu().numpy().astype(np.int32), initial_spins(31, np.arange(2 * S), 64, 1))
+    whole = GS(gm, (8, 8), 5, 2 * S, 1, seed=31, chain_id0=0)
+    full = whole.mcmc_op().cpu().numpy()
+    parts = []
+    for rank in range(2):
+        smp = GS(gm, (8, 8), 5, S, 1, seed=31, chain_id0=rank * S)
+        parts.append(smp.mcmc_op().cpu().numpy())
+    assert np.array_equal(np.concatenate(parts), full)
+    assert len({r.tobytes() for r in full}) > S          # the ranks do not repeat each other's chains
 
 
 def test_sweep_sample_writeout_order():
