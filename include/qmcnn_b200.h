@@ -60,8 +60,25 @@ typedef struct {
     int32_t channels[QMC_MAX_LAYERS]; /* C_1..C_D; CRBM: channels[0] = 2*alpha.
                                          channels[D-1] must be even */
     int32_t Ly, Lx;                   /* system_shape */
-    int32_t reserved[4];              /* zero */
+    int32_t reserved[4];              /* zero = defaults.  Tuning / cross-check knobs (they never change a result
+                                         beyond fp32 rounding of a final sum; tests use them to run every
+                                         decomposition):
+                                           [0] QMC_FLAG_* bits
+                                           [1] max warps per CTA of the persistent kernels (0 = as many as fit)
+                                           [2] warps per phase group of k_sweep_ip (0 = 4)
+                                           [3] max chunks per chain of the time-sliced sweep (0 = 64) */
 } qmc_model_desc;
+
+enum {
+    QMC_FLAG_GENERIC_CONV = 1,      /* generic conv loop instead of the register-tiled FFMA2 instances */
+    QMC_FLAG_SWEEP_CLASSIC = 2,     /* sweep: never the in-place kernel (k_sweep_ip) */
+    QMC_FLAG_SWEEP_INPLACE = 4,     /* sweep: k_sweep_ip whenever the model is inside its coverage */
+    QMC_FLAG_IP_FREE_RUNNING = 8,   /* k_sweep_ip without phase-group barriers (diagnosis) */
+    QMC_FLAG_ENERGY_CLASSIC = 16,   /* TFIM local energy: classic persistent kernel */
+    QMC_FLAG_ENERGY_INPLACE = 32,   /* TFIM local energy: k_energy_ip whenever covered */
+    QMC_FLAG_BACKWARD_GENERIC = 64, /* gradient: k_backward (planes in L2) instead of k_backward_smem */
+    QMC_FLAG_IP_ROWMAJOR_SITES = 128 /* in-place evaluator: row-major site order instead of the conflict-free deal */
+};
 
 typedef struct qmc_handle qmc_handle;
 

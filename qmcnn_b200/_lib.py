@@ -13,6 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libqmcnn_b200.so")
 QMC_MAX_LAYERS = 16
 MODEL_CRBM, MODEL_DCRBM = 0, 1
 TFIM, HEISENBERG = 0, 1
+# tuning / cross-check knobs of a handle (include/qmcnn_b200.h: QMC_FLAG_*, qmc_model_desc.reserved)
+FLAG_GENERIC_CONV, FLAG_SWEEP_CLASSIC, FLAG_SWEEP_INPLACE, FLAG_IP_FREE_RUNNING = 1, 2, 4, 8
+FLAG_ENERGY_CLASSIC, FLAG_ENERGY_INPLACE, FLAG_BACKWARD_GENERIC, FLAG_IP_ROWMAJOR_SITES = 16, 32, 64, 128
 
 
 class QmcError(RuntimeError):
@@ -115,12 +118,18 @@ def check(handle, rc, what):
 class Handle(object):
     """One qmc_handle: a model on one lattice shape on one device."""
 
-    def __init__(self, kind, k, channels, Ly, Lx, device):
+    def __init__(self, kind, k, channels, Ly, Lx, device, tuning=None):
+        """``tuning``: dict with any of flags (FLAG_* bits), max_warps, ip_group, ip_chunks -> desc.reserved."""
         lib = load()
         d = ModelDesc()
         d.kind, d.k, d.n_layers, d.Ly, d.Lx = kind, k, len(channels), Ly, Lx
         for i, c in enumerate(channels):
             d.channels[i] = c
+        tuning = dict(tuning or {})
+        for i, key in enumerate(("flags", "max_warps", "ip_group", "ip_chunks")):
+            d.reserved[i] = int(tuning.pop(key, 0))
+        if tuning:
+            raise QmcError("unknown tuning keys: %s" % sorted(tuning))
         self._h = _vp()
         rc = lib.qmc_create(C.byref(self._h), device, C.byref(d))
         if rc != 0:

@@ -1,5 +1,4 @@
 // qmc_api.cu - the extern "C" boundary declared in include/qmcnn_b200.h.
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "qmc_host.h"
@@ -54,7 +53,6 @@ static bool build_model(const qmc_model_desc* d, DevModel& m, std::string& err) 
     if (m.bias_vis_off >= 0) { m.sp_vis_off = soff; soff += 4; }
     m.P = off;
     m.smem_param_floats = round4(soff);
-    m.use_const = m.smem_param_floats <= kConstFloats ? 1 : 0;
     m.fre_off = coff; coff += round4(m.n);
     m.fim_off = coff; coff += round4(m.n);
     m.cache_floats = coff;
@@ -121,39 +119,27 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     cudaGetDeviceProperties(&prop, device);
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = prop.sharedMemPerBlockOptin;
-    const char* fg = std::getenv("QMC_FORCE_GENERIC");
-    h->allow_tiled = !(fg && fg[0] == '1');
+    // tuning / cross-check knobs (include/qmcnn_b200.h: qmc_model_desc.reserved)
+    const int flags = desc->reserved[0];
+    h->allow_tiled = !(flags & QMC_FLAG_GENERIC_CONV);
+    h->allow_ip = !(flags & QMC_FLAG_SWEEP_CLASSIC);
+    h->force_ip = (flags & QMC_FLAG_SWEEP_INPLACE) != 0;
+    h->ip_sync = (flags & QMC_FLAG_IP_FREE_RUNNING) ? 0 : 3;
+    h->ip_cf = !(flags & QMC_FLAG_IP_ROWMAJOR_SITES);
+    h->energy_path = (flags & QMC_FLAG_ENERGY_CLASSIC) ? 1 : (flags & QMC_FLAG_ENERGY_INPLACE) ? 2 : 0;
+    h->backward_generic = (flags & QMC_FLAG_BACKWARD_GENERIC) != 0;
+    h->max_warps_override = desc->reserved[1] > 0 ? desc->reserved[1] : 0;
+    h->ip_group = desc->reserved[2] > 0 ? desc->reserved[2] : 4;
+    h->ip_chunks = desc->reserved[3] > 0 ? desc->reserved[3] : 64;
     e = cudaMalloc(&h->d_params, sizeof(float) * (size_t)m.P);
     if (e == cudaSuccess) e = cudaMemset(h->d_params, 0, sizeof(float) * (size_t)m.P);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_params_padded, sizeof(float) * (size_t)m.smem_param_floats);
     if (e == cudaSuccess) e = cudaMemset(h->d_params_padded, 0, sizeof(float) * (size_t)m.smem_param_floats);
-    const char* fp = std::getenv("QMC_FORCE_PERSISTENT");
-    h->allow_batched = !(fp && fp[0] == '1');
-    const char* nl = std::getenv("QMC_LEAN");      // opt-in: measured slower than the classic kernel
-    h->allow_lean = nl && nl[0] == '1';
-    const char* mw = std::getenv("QMC_MAX_WARPS");
-    h->max_warps_override = mw ? std::atoi(mw) : 0;
-    const char* sp = std::getenv("QMC_SWEEP_PATH");
-    h->batched_sweep = h->allow_batched && sp && std::strcmp(sp, "batched") == 0;
-    h->allow_ip = !(sp && std::strcmp(sp, "pingpong") == 0);
-    h->force_ip = sp && std::strcmp(sp, "inplace") == 0;
-    const char* is = std::getenv("QMC_IP_SYNC");
-    if (is) h->ip_sync = std::atoi(is);
-    const char* ig = std::getenv("QMC_IP_GROUP");
-    if (ig) h->ip_group = std::atoi(ig);
-    const char* icf = std::getenv("QMC_IP_CF");
-    if (icf) h->ip_cf = std::atoi(icf) != 0;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
-    }
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming);
     if (e == cudaSuccess) e = ip_upload_tables(h);
     cudaSetDevice(prev);
-    if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaMalloc(params)"); }
+    if (e != cudaSuccess) { qmc_destroy(h); return cuda_fail(nullptr, e, "cudaMalloc(params)"); }
     if ((size_t)m.smem_param_floats * 4 > h->max_smem) {
-        cudaFree(h->d_params); cudaFree(h->d_params_padded); delete h;
+        qmc_destroy(h);
         return fail(nullptr, QMC_ERR_UNSUPPORTED, "parameters do not fit in shared memory");
     }
     *out = h;
@@ -169,12 +155,6 @@ int qmc_destroy(qmc_handle* h) {
     cudaFree(h->d_params_padded);
     cudaFree(h->d_sym_padded);
     cudaFree(h->d_ip_tab);
-    for (int i = 0; i < 2; ++i) {
-        if (h->side_stream[i]) cudaStreamDestroy(h->side_stream[i]);
-        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
-    }
-    if (h->ev_in) cudaEventDestroy(h->ev_in);
-    if (h->ev_mid) cudaEventDestroy(h->ev_mid);
     cudaSetDevice(prev);
     delete h;
     return QMC_OK;
@@ -197,27 +177,13 @@ size_t qmc_sweep_workspace_floats(const qmc_handle* h, int S, int num_flips) {
             const size_t b = (size_t)il.grid * il.warps * il.ip.staging_floats;
             if (b > f) f = b;
         }
-        const LeanLaunch ll = lean_launch_plan(h, S);
-        if (ll.ok) {
-            const size_t b = (size_t)ll.grid * ll.warps * ll.staging_floats;
-            if (b > f) f = b;
-        }
-    }
-    if (num_flips == 1 && h->batched_sweep && batched_supported(h)) {
-        const int half = (S + 1) / 2;     // the chains may be split over two streams, each with its own scratch
-        const size_t b = 2 * (batched_staging_floats(h, half) + batched_scratch_floats(half)) + 16;
-        if (b > f) f = b;
     }
     return f ? f : 4;
 }
 
 size_t qmc_energy_workspace_floats(const qmc_handle* h, int N) {
     if (!h || N < 1) return 0;
-    size_t f = (size_t)N * h->m.cache_floats + (size_t)N * energy_chunks(h) * 2;
-    if (h->allow_batched && batched_supported(h))   // + per-site terms and one chunk of staged windows
-        f += (size_t)N * h->m.n * 2 + batched_staging_floats(h, kEnergyChunkItems) +
-             batched_scratch_floats(kEnergyChunkItems);
-    return f;
+    return (size_t)N * h->m.cache_floats + (size_t)N * energy_chunks(h) * 2;
 }
 
 size_t qmc_backward_workspace_floats(const qmc_handle* h, int N) {
@@ -294,14 +260,9 @@ int qmc_metropolis_sweep(qmc_handle* h, int8_t* spins, float* cache, float* work
                     seed, chain_id0, therm_its, its_per_sample > 0 ? its_per_sample : 1, samples,
                     n_sample_slots, accept_trace, logratio_trace, n_accept};
         cudaError_t e;
-        LeanLaunch ll{};
         IpLaunch il{};
-        if (num_flips == 1 && h->batched_sweep && batched_supported(h))
-            e = launch_sweep_batched(h, a, (cudaStream_t)stream, h->err);
-        else if (num_flips == 1 && !h->allow_lean && (il = ip_launch_plan(h, S)).ok)
+        if (num_flips == 1 && (il = ip_launch_plan(h, S)).ok)
             e = launch_sweep_ip(h, a, il, (cudaStream_t)stream);
-        else if (num_flips == 1 && (ll = lean_launch_plan(h, S)).ok)
-            e = launch_sweep_lean(h, a, ll, (cudaStream_t)stream);
         else
             e = launch_sweep(h, a, (cudaStream_t)stream, h->err);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep");

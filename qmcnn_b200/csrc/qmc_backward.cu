@@ -11,8 +11,6 @@
 // parameter gradient is accumulated per CTA in shared memory and the CTAs'
 // partial vectors are summed in a fixed order by k_backward_reduce, so the
 // result is deterministic for a given launch geometry.
-#include <cstdlib>
-#include <cstring>
 #include "qmc_host.h"
 
 namespace qmc {
@@ -363,10 +361,9 @@ __global__ void k_backward_reduce(const float* __restrict__ partial, int nparts,
 
 static int gplane(const DevModel& m);
 
-// shared memory of k_backward_smem, or 0 when the planes do not fit / QMC_BACKWARD=generic
+// shared memory of k_backward_smem, or 0 when the planes do not fit / QMC_FLAG_BACKWARD_GENERIC
 static size_t backward_smem_bytes(const qmc_handle* h) {
-    const char* e = std::getenv("QMC_BACKWARD");           // "generic": force the L2-resident k_backward
-    if (e && std::strcmp(e, "generic") == 0) return 0;
+    if (h->backward_generic) return 0;                     // force the L2-resident k_backward (cross-check)
     const DevModel& m = h->m;
     int c = 1;
     for (int l = 0; l < m.D; ++l) c = c > m.layer[l].coutp ? c : m.layer[l].coutp;

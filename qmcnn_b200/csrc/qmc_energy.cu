@@ -6,8 +6,6 @@
 // and running the full network on each, a warp evaluates each flipped
 // configuration incrementally against the sample's activation cache (filled by
 // K1) and accumulates exp(log_pop) in registers.
-#include <cstdlib>
-#include <cstring>
 #include "qmc_host.h"
 
 // Compiled four times (Makefile): QMC_MAXW=8 (255 registers) / 16 (128 registers) like qmc_sweep.cu, times
@@ -188,26 +186,14 @@ cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, c
     float2* partial = reinterpret_cast<float2*>(workspace + (size_t)N * m.cache_floats);
     cudaError_t e = launch_forward(h, spins, N, cache, nullptr, nullptr, st, err);
     if (e != cudaSuccess) return e;
-    // QMC_ENERGY_PATH=inplace|batched|persistent picks the TFIM decomposition (all agree to rounding of the
-    // final sums); default: see below
-    const char* ep = std::getenv("QMC_ENERGY_PATH");
-    // default for TFIM: the in-place persistent kernel when the model is inside its coverage and big enough for
-    // it to be the sweep's choice too (49.7k vs 47.9k energies/s at C3), else the batched kernels, else the
-    // classic persistent kernel
-    const bool forced_ip = ep && std::strcmp(ep, "inplace") == 0;
-    const bool want_ip = forced_ip || (!ep && ip_launch_plan(h, 1 << 20).ok);
+    // TFIM: the in-place persistent kernel (k_energy_ip) when the model is inside its coverage and big enough for
+    // it to be the sweep's choice too, else the classic persistent kernel; QMC_FLAG_ENERGY_* force one of the two
+    // (the two add the same per-chunk terms in the same order: equal bits)
+    const bool want_ip = h->energy_path == 2 || (h->energy_path == 0 && ip_launch_plan(h, 1 << 20).ok);
     if (!heis && want_ip && energy_ip_supported(h)) {
         e = launch_energy_ip(h, spins, N, cache, partial, nchunks, st);
         if (e != cudaSuccess) return e;
         return launch_energy_finish(h, spins, N, hamiltonian, field_h, partial, nchunks, e_loc, moments, st);
-    }
-    if (!heis && h->allow_batched && batched_supported(h) && !(ep && std::strcmp(ep, "persistent") == 0)) {
-        // layer-synchronous batched evaluation of all N * n single-flip configurations
-        float2* terms = partial + (size_t)N * nchunks;
-        float* scratch = reinterpret_cast<float*>(terms + (size_t)N * m.n);
-        e = launch_energy_batched(h, spins, N, cache, scratch, kEnergyChunkItems, terms, st, err);
-        if (e != cudaSuccess) return e;
-        return launch_energy_finish(h, spins, N, hamiltonian, field_h, terms, m.n, e_loc, moments, st);
     }
     EvalPlan pl = eval_plan(m, h0, h0, true);
     WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, (long long)N * nchunks);

@@ -16,21 +16,19 @@ struct qmc_handle {
     std::string err;
     int num_sms = 0;
     size_t max_smem = 0;   // opt-in dynamic shared memory per CTA
-    bool allow_tiled = true;  // QMC_FORCE_GENERIC=1 disables the specialised conv instances
-    int max_warps_override = 0;  // QMC_MAX_WARPS: tuning knob, caps the warps per CTA of the persistent kernels
-    bool allow_lean = false;     // QMC_LEAN=1: lean persistent sweep kernel (more warps, smaller tiles); off by default
-    bool allow_ip = true;        // QMC_SWEEP_PATH=pingpong disables the in-place persistent sweep kernel (k_sweep_ip)
-    int ip_group = 4;            // QMC_IP_GROUP: warps per phase group of k_sweep_ip<3>
-    int ip_sync = 3;             // QMC_IP_SYNC: 0 = k_sweep_ip's warps run free, otherwise (default) a named barrier per
+    // tuning / cross-check knobs, from qmc_model_desc.reserved (include/qmcnn_b200.h: QMC_FLAG_*)
+    bool allow_tiled = true;     // !QMC_FLAG_GENERIC_CONV: the specialised register-tiled conv instances
+    int max_warps_override = 0;  // reserved[1]: caps the warps per CTA of the persistent kernels
+    bool allow_ip = true;        // !QMC_FLAG_SWEEP_CLASSIC: the in-place persistent sweep kernel (k_sweep_ip) may be chosen
+    bool force_ip = false;       // QMC_FLAG_SWEEP_INPLACE: use k_sweep_ip whenever the model is inside its coverage
+    int ip_group = 4;            // reserved[2]: warps per phase group of k_sweep_ip<3>
+    int ip_sync = 3;             // 0 (QMC_FLAG_IP_FREE_RUNNING): k_sweep_ip's warps run free; 3: a named barrier per
                                  // layer within each phase group of ip_group warps
-    bool ip_cf = true;           // conflict-free site tables for the in-place evaluator (QMC_IP_CF=0: the r01 order)
+    int ip_chunks = 64;          // reserved[3]: at most this many chunks per chain of the time-sliced sweep
+    bool ip_cf = true;           // !QMC_FLAG_IP_ROWMAJOR_SITES: conflict-free site tables for the in-place evaluator
     unsigned short* d_ip_tab = nullptr;   // device image of the tables (ip_upload_tables), or nullptr
-    bool force_ip = false;       // QMC_SWEEP_PATH=inplace: use k_sweep_ip whenever the model is inside its coverage
-    bool allow_batched = true;  // QMC_FORCE_PERSISTENT=1 disables the layer-synchronous batched path (energy + sweep)
-    bool batched_sweep = false; // QMC_SWEEP_PATH=batched: use the batched path for the sweep too (default: persistent
-                                // kernel, which is faster at a few thousand chains per GPU - DESIGN.md)
-    cudaStream_t side_stream[2] = {nullptr, nullptr};   // batched sweep: capturable streams, event-ordered with the caller's
-    cudaEvent_t ev_in = nullptr, ev_mid = nullptr, ev_out[2] = {nullptr, nullptr};
+    int energy_path = 0;         // 0 auto, 1 classic persistent (QMC_FLAG_ENERGY_CLASSIC), 2 in-place (QMC_FLAG_ENERGY_INPLACE)
+    bool backward_generic = false;   // QMC_FLAG_BACKWARD_GENERIC
 };
 
 namespace qmc {
@@ -86,43 +84,6 @@ inline bool box_supported(const DevModel& m, int h0, int w0) {
     return h0 + 2 * m.D * m.p <= m.Ly && w0 + 2 * m.D * m.p <= m.Lx;
 }
 
-// shared-memory plan of warp_eval_flip_lean for a per-warp arena of at most budget_floats
-inline LeanPlan lean_plan(const DevModel& m, int budget_floats) {
-    LeanPlan best{};
-    best.ok = 0;
-    if (m.D < 2 || m.r > m.Ly || m.r > m.Lx) return best;
-    const int p = m.p;
-    for (int fg = m.D - 1; fg >= 1; --fg) {            // prefer as few gathering layers as possible
-        LeanPlan lp{};
-        lp.first_gather = fg;
-        int bufa = 0, bufb = 0;
-        for (int l = 0; l < fg; ++l) {                 // chained tiles alternate between the two buffers
-            const int tside = 1 + 2 * (l + 1) * p + 2 * p;
-            const int t = tside * tside * m.layer[l].cinp;
-            int& dst = (l & 1) ? bufb : bufa;
-            dst = dst > t ? dst : t;
-        }
-        lp.off_b = round4(bufa);
-        int need = round4(bufa) + round4(bufb);
-        bool ok = need <= budget_floats;
-        for (int l = fg; l < m.D && ok; ++l) {
-            const int side = 1 + 2 * (l + 1) * p, tside = side + 2 * p;
-            const bool last = l == m.D - 1;
-            int nb = 0;
-            for (int b = 1; b <= 4; ++b) {
-                const int rows = (side + b - 1) / b;
-                int t = round4((rows + 2 * p) * tside * m.layer[l].cinp);
-                if (last) t += round4(rows * side * m.layer[l].coutp);
-                if (t <= budget_floats) { nb = b; need = need > t ? need : t; break; }
-            }
-            if (!nb) ok = false;
-            lp.bands[l] = nb;
-        }
-        if (ok) { lp.arena_floats = round4(need); lp.ok = 1; return lp; }
-    }
-    return best;
-}
-
 struct WarpGrid { int grid, warps; size_t smem; bool ok; };
 
 // one CTA per SM, W warps, W chosen to minimise the idle tail over `units` warp tasks
@@ -168,9 +129,6 @@ cudaError_t repack_params(const qmc_handle* h, cudaStream_t st);
 cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
                            float* factors, float* logpsi, cudaStream_t st, std::string& err);
 cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
-struct LeanLaunch { LeanPlan lp; int warps, grid; size_t smem; int newf_floats, spins_bytes, staging_floats; bool ok; };
-LeanLaunch lean_launch_plan(const qmc_handle* h, int S);
-cudaError_t launch_sweep_lean(const qmc_handle* h, const SweepArgs& a, const LeanLaunch& ll, cudaStream_t st);
 struct IpLaunch { IpPlan ip; int warps, grid; size_t smem; bool ok; };
 IpPlan ip_plan(const qmc_handle* h);
 cudaError_t ip_upload_tables(qmc_handle* h);
@@ -190,15 +148,6 @@ cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const floa
                             float* workspace, float* grad, cudaStream_t st, std::string& err);
 
 int sweep_slots(const qmc_handle* h, int S, int num_flips, EvalPlan* plan, WarpGrid* grid);
-// layer-synchronous batched path (qmc_batched.cu)
-bool batched_supported(const qmc_handle* h);
-size_t batched_staging_floats(const qmc_handle* h, int n_items);
-size_t batched_scratch_floats(int n_items);
-cudaError_t launch_sweep_batched(const qmc_handle* h, const SweepArgs& s, cudaStream_t caller, std::string& err);
-cudaError_t launch_energy_batched(const qmc_handle* h, const int8_t* spins, int N, const float* cache,
-                                  float* scratch, int chunk_items, float2* terms, cudaStream_t st,
-                                  std::string& err);
-constexpr int kEnergyChunkItems = 32768;   // (sample, site) items evaluated per batched pass
 cudaError_t launch_energy_finish(const qmc_handle* h, const int8_t* spins, int N, int hamiltonian, float field_h,
                                  const float2* partial, int nchunks, float* e_loc, double* moments,
                                  cudaStream_t st);

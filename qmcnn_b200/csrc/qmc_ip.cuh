@@ -97,7 +97,7 @@ __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const 
     const int npos = side * side;
     constexpr int PMAX = ACC / COUT;
     auto o = [&](int, int pos, int y, int x, int cog, float4 a) { out(pos, y, x, cog, a); };
-#define QMC_TILED(PP) conv_region_tiled<K, CIN, COUT, (PP), false, 1>(wbase, bbase, wsm, tin, 0, tw, tarea, side, side, lane, o, mid, tab)
+#define QMC_TILED(PP) conv_region_tiled<K, CIN, COUT, (PP), 1>(wbase, bbase, wsm, tin, 0, tw, tarea, side, side, lane, o, mid, tab)
     if (PMAX == 1 || npos <= 32) return QMC_TILED(1);
     if (PMAX == 2 || npos <= 64) return QMC_TILED(2);
     if (PMAX == 3 || npos <= 96) return QMC_TILED(PMAX >= 3 ? 3 : 2);

@@ -5,7 +5,6 @@
 // instead of 1.75 - the classic kernel issues on only 44% of cycles because each scheduler has
 // fewer than two warps to choose from).  Single-flip proposals of deep k = 3 models whose
 // windows fit one round of the register tile; everything else runs the classic kernel.
-#include <cstdlib>
 #include <vector>
 #include "qmc_host.h"
 #include "qmc_ip.cuh"
@@ -345,8 +344,7 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
     // time slicing: chunks of >= 64 steps, at most 64 chunks per chain; one chunk when S fits the slots
     long long chunks = 1;
     if ((long long)a.S > slots) {
-        const char* ce = std::getenv("QMC_IP_CHUNKS");      // tuning knob: at most this many chunks per chain
-        const long long cmax = ce && std::atoi(ce) > 0 ? std::atoi(ce) : 64;
+        const long long cmax = h->ip_chunks > 0 ? h->ip_chunks : 64;     // at most this many chunks per chain
         chunks = a.n_steps / 64;
         if (chunks > cmax) chunks = cmax;
         if (chunks < 1) chunks = 1;

@@ -36,6 +36,9 @@ class _Model(object):
             self.params[n] = self.flat[o:o + size].view(*s)
             o += size
         self._handles = {}
+        # tuning / cross-check knobs for the handles this model creates (dict: flags = _lib.FLAG_* bits,
+        # max_warps, ip_group, ip_chunks); defaults when empty.  Tests use it to run every decomposition.
+        self.tuning = {}
 
     @property
     def num_params(self):
@@ -50,12 +53,13 @@ class _Model(object):
         if len(system_shape) != 2 or self.n_dims != 2:
             raise _lib.QmcError("this call is covered by the tuned 2-D kernels only (n_dims == 2); 1-D / 3-D "
                                 "lattices have factors, Sampler and the energy estimators (qmc_nd_*)")
-        h = self._handles.get(system_shape)
+        key = (system_shape, tuple(sorted(self.tuning.items())))
+        h = self._handles.get(key)
         if h is None:
             h = _lib.Handle(self._kind, self.k, self._channels, system_shape[0], system_shape[1],
-                            self.device.index or 0)
+                            self.device.index or 0, self.tuning)
             assert h.num_params == self.flat.numel()
-            self._handles[system_shape] = h
+            self._handles[key] = h
         _lib.check(h.ptr, _lib.load().qmc_set_params(h.ptr, self.flat.data_ptr(),
                                                      _stream_ptr(self.device)), "qmc_set_params")
         return h

@@ -8,6 +8,80 @@
 #include "qmc_device.cuh"
 using namespace qmc;
 
+// Parameter block in constant memory: weight reads with warp-uniform addresses compile to LDCU into uniform
+// registers and FFMA2 takes the weight pair as a uniform operand (FFMA2 R, R.F32, UR.F32x2, R): no LDS, no vector
+// registers, no shared memory for weights.  ptxas does this only in a kernel that contains nothing but the conv
+// (here); inside the persistent product kernels it falls back to per-lane LDC (profiles/r01_summary.md), which is
+// why the product's conv_region_tiled reads its weights from shared memory.
+constexpr int kConstFloats = 15360;
+static __constant__ float c_params[kConstFloats];
+
+// conv_region_tiled (qmc_device.cuh) with the weights taken from c_params
+template <int K, int CIN, int COUT, int P, typename OutF>
+__device__ __forceinline__ void conv_region_const(int wbase, int bbase, const float* tin, int tw, int tarea, int rh,
+                                                  int rw, int lane, OutF out) {
+    constexpr int NCG = CIN / 4;
+    const int npos = rh * rw, G = (npos + P - 1) / P;
+    const float4* tin4 = reinterpret_cast<const float4*>(tin);
+    const FastDiv drw(rw);
+    for (int g0 = 0; g0 < G; g0 += kWarp) {
+        const bool lane_on = g0 + lane < G;
+        const int g = lane_on ? g0 + lane : 0;
+        int toff[P], ys[P], xs[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            int pos = g + j * G;
+            if (pos >= npos) pos = g;
+            ys[j] = drw.div(pos);
+            xs[j] = pos - ys[j] * rw;
+            toff[j] = ys[j] * tw + xs[j];
+        }
+        float2 acc[P][COUT / 2];
+#pragma unroll
+        for (int q2 = 0; q2 < COUT / 2; ++q2) {
+            const float2 b = make_float2(c_params[bbase + 2 * q2], c_params[bbase + 2 * q2 + 1]);
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[j][q2] = b;
+        }
+#pragma unroll 1
+        for (int d = 0; d < K * K; ++d) {
+            const int dy = d / K, dx = d - dy * K;
+            const float4* tp = tin4 + dy * tw + dx;
+            const int wrow = wbase + d * CIN * COUT;
+#pragma unroll 1
+            for (int cg = 0; cg < NCG; ++cg) {
+                float4 in[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j) in[j] = tp[cg * tarea + toff[j]];
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float2 w[COUT / 2];
+#pragma unroll
+                    for (int q2 = 0; q2 < COUT / 2; ++q2) {
+                        const int wi = wrow + (cg * 4 + c4) * COUT + q2 * 2;   // warp-uniform -> LDCU
+                        w[q2] = make_float2(c_params[wi], c_params[wi + 1]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < P; ++j) {
+                        const float v = c4 == 0 ? in[j].x : c4 == 1 ? in[j].y : c4 == 2 ? in[j].z : in[j].w;
+                        const float2 v2 = make_float2(v, v);
+#pragma unroll
+                        for (int q2 = 0; q2 < COUT / 2; ++q2) acc[j][q2] = __ffma2_rn(v2, w[q2], acc[j][q2]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int pos = g + j * G;
+            if (!lane_on || pos >= npos) continue;
+#pragma unroll
+            for (int q4 = 0; q4 < COUT / 4; ++q4)
+                out(pos, ys[j], xs[j], q4, make_float4(acc[j][q4 * 2].x, acc[j][q4 * 2].y, acc[j][q4 * 2 + 1].x, acc[j][q4 * 2 + 1].y));
+        }
+    }
+}
+
 template <int P, int COUT>
 __global__ void __launch_bounds__(512, 1)
 k_layer(const float* __restrict__ in_tiles, float* __restrict__ out, int n_items, int rh, int rw, int wbase, int bbase) {
@@ -23,8 +97,8 @@ k_layer(const float* __restrict__ in_tiles, float* __restrict__ out, int n_items
         cp_async_wait_all();
         __syncwarp();
         float4* o4 = reinterpret_cast<float4*>(out + (size_t)item * rarea * COUT);
-        conv_region_tiled<3, 16, COUT, P, true, 1>(wbase, bbase, nullptr, tile, 0, tw, tarea, rh, rw, lane,
-            [&](int, int pos, int, int, int cog, float4 a) {
+        conv_region_const<3, 16, COUT, P>(wbase, bbase, tile, tw, tarea, rh, rw, lane,
+            [&](int pos, int, int, int cog, float4 a) {
                 a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
                 o4[cog * rarea + pos] = a;
             });

@@ -50,22 +50,21 @@ def energy(case, model, states):
 SWEEPABLE = sorted(CASES)       # incl. heis_dcrbm: two flips of a deep model run the generic full-forward path
 
 
-@pytest.fixture(params=["default", "inplace", "pingpong", "batched"])
+@pytest.fixture(params=["default", "inplace", "classic", "inplace-rowmajor"])
 def sweep_path(request):
     """Every sweep decomposition must reproduce the reference's chains: the default choice, the in-place
-    persistent kernel forced on (k_sweep_ip; it is the default only for big models), the classic ping-pong
-    kernel, and the layer-synchronous batched kernels (each falls back to the classic kernel for shapes it
-    does not cover, e.g. CRBM or two flips)."""
-    if request.param != "default":
-        os.environ["QMC_SWEEP_PATH"] = request.param
-    yield request.param
-    os.environ.pop("QMC_SWEEP_PATH", None)
+    persistent kernel forced on (k_sweep_ip; it is the default only for big models; with the conflict-free site
+    deal and with the row-major order) and the classic ping-pong kernel (each falls back to the classic
+    kernel for shapes it does not cover, e.g. CRBM or two flips).  Returns the model tuning dict."""
+    return {"default": {}, "inplace": dict(flags=q.FLAG_SWEEP_INPLACE), "classic": dict(flags=q.FLAG_SWEEP_CLASSIC),
+            "inplace-rowmajor": dict(flags=q.FLAG_SWEEP_INPLACE | q.FLAG_IP_ROWMAJOR_SITES)}[request.param]
 
 
 @pytest.mark.parametrize("name", SWEEPABLE)
 def test_mcmc_op_reproduces_reference_chain(name, sweep_path):
     case, g = CASES[name], load(name)
     model = build(case["model"], g)
+    model.tuning = dict(sweep_path)
     smp = make_sampler(case, model)
     assert [smp.num_samplers, smp.its_per_sample, smp.samples_per_sampler, smp.therm_its, smp.sample_its,
             smp.padded_size] == list(g["bookkeeping"])

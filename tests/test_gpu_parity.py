@@ -119,13 +119,10 @@ def test_specialised_conv_is_bit_identical_to_generic():
     shape = (13, 14)
     s = torch.as_tensor(rand_states(np.random.default_rng(3), 5, shape))
     outs = []
-    for force in ("0", "1"):
-        os.environ["QMC_FORCE_GENERIC"] = force
-        try:
-            gm, _ = make_pair("dcrbm", 13, 1e-1, 77, layers=[16, 16, 16, 8])
-            outs.append(gm.forward_unpadded(s, shape)[0].cpu().numpy())
-        finally:
-            os.environ.pop("QMC_FORCE_GENERIC", None)
+    for flags in (0, _q().FLAG_GENERIC_CONV):
+        gm, _ = make_pair("dcrbm", 13, 1e-1, 77, layers=[16, 16, 16, 8])
+        gm.tuning = dict(flags=flags)
+        outs.append(gm.forward_unpadded(s, shape)[0].cpu().numpy())
     assert np.array_equal(outs[0].view(np.float32), outs[1].view(np.float32))
 
 
@@ -378,82 +375,6 @@ def test_incremental_cache_equals_full_forward_after_many_flips():
     assert a.acceptance_count > 0
 
 
-@pytest.mark.parametrize("layers,shape,S", [([16, 16, 16, 8], (12, 13), 70), ([8, 8, 8], (10, 10), 33),
-                                            ([16, 16, 16, 16, 16, 8], (20, 20), 21)])
-def test_batched_path_is_bit_identical_to_persistent(layers, shape, S):
-    """The layer-synchronous batched kernels (uniform-register weights, CUDA graph) and the
-    persistent warp-per-chain kernel must produce identical bits: accept decisions, log-ratios,
-    final states, samples and local energies."""
-    from gpu_util import make_pair
-    q = _q()
-    r = len(layers) * 2 + 1
-    outs = []
-    for force in ("1", "0"):
-        os.environ["QMC_FORCE_PERSISTENT"] = force      # "1": persistent kernels for sweep and energy
-        os.environ["QMC_SWEEP_PATH"] = "batched"         # "0": batched kernels for sweep and energy
-        try:
-            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 17, layers=layers)
-
-            class GS(q.Sampler):
-                MAX_NUM_SAMPLERS = 10 ** 9
-                SWEEPFACTOR, THERMFACTOR = 1, 1
-            init = (np.random.default_rng(3).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
-            smp = GS(gm, shape, r, 2 * S, 1, seed=99, chain_id0=5)     # 2 samples per chain
-            smp.MAX_NUM_SAMPLERS = S
-            smp = type("GS2", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))(
-                gm, shape, r, 2 * S, 1, seed=99, chain_id0=5)
-            smp.feed(initial_states=init)
-            samples = smp.mcmc_op(trace=True)            # > 64 steps: exercises the CUDA-graph blocks + remainder
-            e = q.ising_energy(gm, samples, system_shape=shape, H=1.3)
-            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(),
-                         samples.clone(), e.clone(), smp.acceptance_count, smp.sample_its))
-        finally:
-            os.environ.pop("QMC_FORCE_PERSISTENT", None)
-            os.environ.pop("QMC_SWEEP_PATH", None)
-    a, b = outs
-    assert a[6] == b[6] and a[6] > 64
-    assert torch.equal(a[0], b[0]), "accept decisions differ"
-    assert torch.equal(a[1], b[1]), "log-ratios differ"
-    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
-    # energies: same per-site terms, summed in a different grouping (8 chunks vs site order)
-    ea, eb = a[4].cpu().numpy(), b[4].cpu().numpy()
-    assert np.abs(ea - eb).max() <= 2e-6 * np.abs(ea).max(), "local energies differ"
-    assert a[5] == b[5] and 0 < a[5] < a[0].numel()
-
-
-@pytest.mark.parametrize("layers,shape,S", [([16, 16, 16, 16, 16, 8], (20, 20), 40), ([8, 8, 8], (10, 10), 50),
-                                            ([3, 5, 6], (9, 8), 17), ([16, 8], (7, 9), 9)])
-def test_lean_kernel_is_bit_identical_to_classic(layers, shape, S):
-    """k_sweep_lean (band-wise re-gathered tiles, 14 warps per SM) against the classic persistent kernel."""
-    from gpu_util import make_pair
-    q = _q()
-    r = len(layers) * 2 + 1
-    outs = []
-    for lean in ("0", "1"):
-        os.environ["QMC_LEAN"] = lean
-        try:
-            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 23, layers=layers)
-            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
-            init = (np.random.default_rng(4).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
-            smp = GS(gm, shape, r, 2 * S, 1, seed=7, chain_id0=11)
-            smp.feed(initial_states=init)
-            samples = smp.mcmc_op(trace=True)
-            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
-                         smp.current_factors_var.clone(), smp._cache.clone()))
-        finally:
-            os.environ.pop("QMC_LEAN", None)
-    a, b = outs
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
-    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
-    assert 0 < int(a[0].sum()) < a[0].numel()
-    # the hidden-layer planes and the Re factor plane of the incrementally maintained caches agree bit for bit
-    h = gm.handle(shape)
-    cf, n = h.cache_floats, shape[0] * shape[1]
-    ca, cb = a[5].view(S, cf), b[5].view(S, cf)
-    used = cf - 2 * ((n + 3) // 4 * 4) + n          # everything up to and including fRe
-    assert torch.equal(ca[:, :used], cb[:, :used])
-
-
 # ----------------------------------------------------------------------------- energy
 @pytest.mark.parametrize("name,kind,shape,kw", CASES[:5], ids=[c[0] for c in CASES[:5]])
 @pytest.mark.parametrize("scale", [1e-2, 1e-1])
@@ -583,19 +504,16 @@ def test_inplace_kernel_is_bit_identical_to_classic(layers, shape, S):
     q = _q()
     r = len(layers) * 2 + 1
     outs = []
-    for path in ("pingpong", "inplace"):
-        os.environ["QMC_SWEEP_PATH"] = path
-        try:
-            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 23, layers=layers)
-            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
-            init = (np.random.default_rng(4).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
-            smp = GS(gm, shape, r, 2 * S, 1, seed=7, chain_id0=11)
-            smp.feed(initial_states=init)
-            samples = smp.mcmc_op(trace=True)
-            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
-                         smp.current_factors_var.clone(), smp._cache.clone()))
-        finally:
-            os.environ.pop("QMC_SWEEP_PATH", None)
+    for flags in (q.FLAG_SWEEP_CLASSIC, q.FLAG_SWEEP_INPLACE):
+        gm, _ = make_pair("dcrbm", shape[0], 2e-1, 23, layers=layers)
+        gm.tuning = dict(flags=flags)
+        GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+        init = (np.random.default_rng(4).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+        smp = GS(gm, shape, r, 2 * S, 1, seed=7, chain_id0=11)
+        smp.feed(initial_states=init)
+        samples = smp.mcmc_op(trace=True)
+        outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
+                     smp.current_factors_var.clone(), smp._cache.clone()))
     a, b = outs
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
@@ -626,12 +544,8 @@ def test_shared_memory_backward_matches_generic_and_oracle(kind, kw, shape):
     w = torch.as_tensor(((e - e.mean()) / N).astype(np.complex64), device="cuda")
     grads = {}
     for mode in ("generic", "smem"):
-        if mode == "generic":
-            os.environ["QMC_BACKWARD"] = "generic"
-        try:
-            grads[mode] = q.logpsi_gradient(gm, torch.as_tensor(states, device="cuda"), w, system_shape=shape).cpu().numpy()
-        finally:
-            os.environ.pop("QMC_BACKWARD", None)
+        gm.tuning = dict(flags=q.FLAG_BACKWARD_GENERIC) if mode == "generic" else {}
+        grads[mode] = q.logpsi_gradient(gm, torch.as_tensor(states, device="cuda"), w, system_shape=shape).cpu().numpy()
     scale = np.abs(grads["generic"]).max()
     assert np.abs(grads["smem"] - grads["generic"]).max() <= 2e-6 * scale
     want, _ = oracle.vmc_gradient(om.astype(np.float64), padded(om, states, shape), e)
@@ -648,26 +562,24 @@ def test_time_sliced_inplace_sweep_is_bit_identical_to_classic(sync, warps, S):
     q = _q()
     layers, shape = [16, 16, 16, 16, 16, 8], (20, 20)      # 11 warps: phase groups of 4, 4, 3; 12 warps: 2.1 waves
     outs = []
-    for path in ("pingpong", "inplace"):
-        os.environ["QMC_SWEEP_PATH"] = path
+    for path in ("classic", "inplace"):
+        gm, _ = make_pair("dcrbm", shape[0], 2e-1, 29, layers=layers)
+        flags = q.FLAG_SWEEP_CLASSIC if path == "classic" else q.FLAG_SWEEP_INPLACE
+        if sync == "0":
+            flags |= q.FLAG_IP_FREE_RUNNING
+        gm.tuning = dict(flags=flags)
         if path == "inplace" or warps == "1":
-            os.environ["QMC_MAX_WARPS"] = warps
-        os.environ["QMC_IP_SYNC"] = sync
-        try:
-            gm, _ = make_pair("dcrbm", shape[0], 2e-1, 29, layers=layers)
-            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
-            init = (np.random.default_rng(6).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
-            smp = GS(gm, shape, 13, 2 * S, 1, seed=3, chain_id0=1000)
-            assert smp.sample_its == 1201                     # 18 chunks of 67 steps, 5994 tasks on 148 slots
-            smp.feed(initial_states=init)
-            launches0 = q.load_library().qmc_launch_count()
-            samples = smp.mcmc_op(trace=True)
-            launches = q.load_library().qmc_launch_count() - launches0
-            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
-                         smp.acceptance_count, launches, smp._cache.clone()))
-        finally:
-            for k in ("QMC_SWEEP_PATH", "QMC_MAX_WARPS", "QMC_IP_SYNC"):
-                os.environ.pop(k, None)
+            gm.tuning["max_warps"] = int(warps)
+        GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+        init = (np.random.default_rng(6).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+        smp = GS(gm, shape, 13, 2 * S, 1, seed=3, chain_id0=1000)
+        assert smp.sample_its == 1201                     # 18 chunks of 67 steps, 5994 tasks on 148 slots
+        smp.feed(initial_states=init)
+        launches0 = q.load_library().qmc_launch_count()
+        samples = smp.mcmc_op(trace=True)
+        launches = q.load_library().qmc_launch_count() - launches0
+        outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
+                     smp.acceptance_count, launches, smp._cache.clone()))
     a, b = outs
     assert b[5] > a[5] + 15, "the in-place run was not time-sliced (%d vs %d launches)" % (b[5], a[5])
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
@@ -681,9 +593,9 @@ def test_time_sliced_inplace_sweep_is_bit_identical_to_classic(sync, warps, S):
 
 @pytest.mark.parametrize("layers,shape,N", [([16, 16, 16, 16, 16, 8], (20, 20), 5), ([8, 8, 8], (10, 10), 33),
                                             ([16, 16, 8], (9, 8), 7), ([16, 8], (7, 9), 300)])
-def test_inplace_energy_kernel_matches_persistent_batched_and_oracle(layers, shape, N):
-    """k_energy_ip (TFIM local energies through the in-place evaluator, QMC_ENERGY_PATH=inplace) against the
-    classic persistent kernel (same per-chunk sums: equal bits), the batched kernels and the oracle."""
+def test_inplace_energy_kernel_matches_persistent_and_oracle(layers, shape, N):
+    """k_energy_ip (TFIM local energies through the in-place evaluator, QMC_FLAG_ENERGY_INPLACE) against the
+    classic persistent kernel (same per-chunk sums: equal bits) and the oracle."""
     import oracle
     from gpu_util import make_pair, rand_states
     q = _q()
@@ -691,16 +603,12 @@ def test_inplace_energy_kernel_matches_persistent_batched_and_oracle(layers, sha
     states = rand_states(np.random.default_rng(12), N, shape)
     st = torch.as_tensor(states, device="cuda")
     out = {}
-    for path in ("inplace", "persistent", "batched"):
-        os.environ["QMC_ENERGY_PATH"] = path
-        try:
-            l0 = q.load_library().qmc_launch_count()
-            out[path] = q.ising_energy(gm, st, system_shape=shape, H=0.7).cpu().numpy()
-            out[path + "_launches"] = q.load_library().qmc_launch_count() - l0
-        finally:
-            os.environ.pop("QMC_ENERGY_PATH", None)
+    for path, flag in (("inplace", q.FLAG_ENERGY_INPLACE), ("persistent", q.FLAG_ENERGY_CLASSIC)):
+        gm.tuning = dict(flags=flag)
+        l0 = q.load_library().qmc_launch_count()
+        out[path] = q.ising_energy(gm, st, system_shape=shape, H=0.7).cpu().numpy()
+        out[path + "_launches"] = q.load_library().qmc_launch_count() - l0
     assert np.array_equal(out["inplace"], out["persistent"]), "in-place and classic persistent energies differ"
-    assert np.abs(out["inplace"] - out["batched"]).max() <= 2e-6 * np.abs(out["batched"]).max()
     want = oracle.ising_energy(om.astype(np.float64), states, shape, om.r, H=0.7)
     assert np.abs(out["inplace"] - want).max() <= 1e-5 * np.abs(want).max()
 
@@ -734,17 +642,14 @@ def test_full_size_c5_shapes():
     S = 1800
     init = rand_states(rng, S, shape)
     outs = []
-    for path in ("pingpong", "inplace"):
-        os.environ["QMC_SWEEP_PATH"] = path
-        try:
-            gm2, _ = make_pair("dcrbm", 40, 1e-1, 1301, layers=layers)
-            GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S))
-            smp = GS(gm2, shape, 13, S, 1, seed=9)
-            smp.feed(initial_states=init)
-            smp.mcmc_op(n_its=150, trace=True)
-            outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone()))
-        finally:
-            os.environ.pop("QMC_SWEEP_PATH", None)
+    for flags in (q.FLAG_SWEEP_CLASSIC, q.FLAG_SWEEP_INPLACE):
+        gm2, _ = make_pair("dcrbm", 40, 1e-1, 1301, layers=layers)
+        gm2.tuning = dict(flags=flags)
+        GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S))
+        smp = GS(gm2, shape, 13, S, 1, seed=9)
+        smp.feed(initial_states=init)
+        smp.mcmc_op(n_its=150, trace=True)
+        outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone()))
     a, b = outs
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     assert 0 < int(a[0].sum()) < a[0].numel()
