@@ -247,6 +247,8 @@ def run_cuda(args, cfg, name):
     import torch.distributed as dist
     import qmcnn_b200 as q
     from qmcnn_b200 import _lib
+    if args.lib:
+        _lib.LIB_PATH = os.path.abspath(args.lib)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -465,6 +467,7 @@ def main():
     ap.add_argument("--ref-chains", type=int, default=256)
     ap.add_argument("--ref-its", type=int, default=256)
     ap.add_argument("--ref-energy", type=int, default=4)
+    ap.add_argument("--lib", default="", help="A/B measurements: load this build of the library instead of the in-tree one")
     ap.add_argument("--sigma", type=float, default=SCALE,
                     help="std of the synthetic parameters (models.py SCALE = 1e-2: acceptance ~ 1; 1e-1: non-trivial)")
     args = ap.parse_args()

@@ -158,6 +158,23 @@ int qmc_metropolis_sweep_sym(qmc_handle* h, int nsym, int8_t* spins, float* cach
                              int8_t* samples, int64_t n_sample_slots, uint8_t* accept_trace,
                              float* logratio_trace, unsigned long long* n_accept, void* stream);
 
+/* The symmetry-averaged amplitude in the other kernels (after qmc_set_image_params with the same nsym).  The
+ * images are an extra grid dimension of the SAME launches:
+ *   forward_sym   caches [nsym, N, qmc_cache_floats] filled for every image; log_rel [N, nsym, 2] fp64 or NULL
+ *                 (= log psi_g - log psi_0, what qmc_metropolis_sweep_sym carries); logpsi_sym [N] complex64 or NULL
+ *                 = log((1/nsym) sum_g psi_g)                                                        (2 launches)
+ *   local_energy_sym   E_loc[psi_sym] = sum_g p_g E_loc[psi_g], p_g = psi_g / sum_h psi_h           (3 launches)
+ *   backward_sym  grad_images [nsym, P] (+=): image g's gradient for the weights w_n conj(p_gn); the caller adds
+ *                 them into the one trainable vector through the image gather index                 (4 launches) */
+size_t qmc_sym_energy_workspace_floats(const qmc_handle* h, int nsym, int N);
+size_t qmc_sym_backward_workspace_floats(const qmc_handle* h, int nsym, int N);
+int qmc_logpsi_forward_sym(qmc_handle* h, int nsym, const int8_t* spins, int N, float* caches, double* log_rel,
+                           float* logpsi_sym, void* stream);
+int qmc_local_energy_sym(qmc_handle* h, int nsym, int hamiltonian, float field_h, const int8_t* spins, int N,
+                         float* workspace, float* e_loc, double* moments, void* stream);
+int qmc_logpsi_backward_sym(qmc_handle* h, int nsym, const int8_t* spins, const float* weights, int N,
+                            float* workspace, float* grad_images, void* stream);
+
 /* ising_energy / heisenberg_energy (mcmc_tf.py:59-90, 93-141): local energy
  * PER SPIN of N samples; all Ly*Lx (TFIM) or 2*Ly*Lx (Heisenberg) connected
  * configurations evaluated as receptive-field deltas in one launch sequence.

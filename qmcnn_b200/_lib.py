@@ -74,6 +74,11 @@ SIGNATURES = {
     "qmc_sym_sweep_workspace_floats": (_sz, [_vp, _i, _i, _i]),
     "qmc_metropolis_sweep_sym": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i64, _i64, _vp, _vp, _u64, _i64,
                                       _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "qmc_sym_energy_workspace_floats": (_sz, [_vp, _i, _i]),
+    "qmc_sym_backward_workspace_floats": (_sz, [_vp, _i, _i]),
+    "qmc_logpsi_forward_sym": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "qmc_local_energy_sym": (_i, [_vp, _i, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
+    "qmc_logpsi_backward_sym": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_local_energy": (_i, [_vp, _i, _f, _vp, _i, _vp, _vp, _vp, _vp]),
     "qmc_logpsi_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_nd_last_error": (C.c_char_p, []),

@@ -279,14 +279,11 @@ int qmc_set_image_params(qmc_handle* h, int nsym, const float* params_images, vo
         cudaError_t e = cudaSuccess;
         if (h->nsym != nsym) {
             cudaFree(h->d_sym_padded);
-    cudaFree(h->d_ip_tab);
             h->d_sym_padded = nullptr;
             e = cudaMalloc(&h->d_sym_padded, sizeof(float) * (size_t)nsym * h->m.smem_param_floats);
             h->nsym = e == cudaSuccess ? nsym : 0;
         }
-        for (int g = 0; g < nsym && e == cudaSuccess; ++g)
-            e = repack_params_to(h, params_images + (size_t)g * h->m.P,
-                                 h->d_sym_padded + (size_t)g * h->m.smem_param_floats, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = repack_params_to(h, params_images, h->d_sym_padded, (cudaStream_t)stream, nsym);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "set_image_params");
     }
     QMC_LEAVE(h);
@@ -326,6 +323,70 @@ int qmc_metropolis_sweep_sym(qmc_handle* h, int nsym, int8_t* spins, float* cach
                     n_sample_slots, accept_trace, logratio_trace, n_accept};
         cudaError_t e = launch_sweep_sym(h, a, nsym, log_rel, (cudaStream_t)stream, h->err);
         if (e != cudaSuccess) rc = cuda_fail(h, e, "metropolis_sweep_sym");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+static int sym_ready(qmc_handle* h, int nsym, const char* what) {
+    if (nsym < 1 || nsym != h->nsym || !h->d_sym_padded)
+        return fail(h, QMC_ERR_BAD_ARGUMENT, std::string(what) + ": call qmc_set_image_params with the same nsym first");
+    return QMC_OK;
+}
+
+size_t qmc_sym_energy_workspace_floats(const qmc_handle* h, int nsym, int N) {
+    if (!h || N < 1 || nsym < 1) return 0;
+    return energy_sym_workspace_floats(h, nsym, N);
+}
+
+size_t qmc_sym_backward_workspace_floats(const qmc_handle* h, int nsym, int N) {
+    if (!h || N < 1 || nsym < 1) return 0;
+    return backward_images_workspace_floats(h, nsym, N);
+}
+
+int qmc_logpsi_forward_sym(qmc_handle* h, int nsym, const int8_t* spins, int N, float* caches, double* log_rel,
+                           float* logpsi_sym, void* stream) {
+    QMC_ENTER(h);
+    int rc = sym_ready(h, nsym, "forward_sym");
+    if (rc == QMC_OK && (N < 0 || (N > 0 && (!spins || !caches)))) rc = fail(h, QMC_ERR_BAD_ARGUMENT, "forward_sym: null spins/caches");
+    if (rc == QMC_OK && N > 0) {
+        cudaError_t e = launch_forward_images(h, nsym, h->d_sym_padded, spins, N, caches, nullptr, nullptr,
+                                              (cudaStream_t)stream, h->err);
+        if (e == cudaSuccess && (log_rel || logpsi_sym))
+            e = launch_sym_logrel(h, nsym, N, caches, log_rel, logpsi_sym, (cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "logpsi_forward_sym");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_local_energy_sym(qmc_handle* h, int nsym, int hamiltonian, float field_h, const int8_t* spins, int N,
+                         float* workspace, float* e_loc, double* moments, void* stream) {
+    QMC_ENTER(h);
+    int rc = sym_ready(h, nsym, "local_energy_sym");
+    if (rc == QMC_OK && (N < 0 || (N > 0 && (!spins || !workspace || !e_loc))))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "local_energy_sym: null spins/workspace/e_loc");
+    else if (rc == QMC_OK && hamiltonian != QMC_HAMILTONIAN_TFIM && hamiltonian != QMC_HAMILTONIAN_HEISENBERG)
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "local_energy_sym: unknown hamiltonian");
+    if (rc == QMC_OK && N > 0) {
+        cudaError_t e = launch_energy_sym(h, nsym, hamiltonian, field_h, spins, N, workspace, e_loc, moments,
+                                          (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "local_energy_sym");
+    }
+    QMC_LEAVE(h);
+    return rc;
+}
+
+int qmc_logpsi_backward_sym(qmc_handle* h, int nsym, const int8_t* spins, const float* weights, int N,
+                            float* workspace, float* grad_images, void* stream) {
+    QMC_ENTER(h);
+    int rc = sym_ready(h, nsym, "backward_sym");
+    if (rc == QMC_OK && (N < 0 || (N > 0 && (!spins || !weights || !workspace)) || !grad_images))
+        rc = fail(h, QMC_ERR_BAD_ARGUMENT, "backward_sym: null argument");
+    if (rc == QMC_OK && N > 0) {
+        cudaError_t e = launch_backward_images(h, nsym, h->d_sym_padded, spins, weights, N, workspace, grad_images,
+                                               (cudaStream_t)stream, h->err);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "logpsi_backward_sym");
     }
     QMC_LEAVE(h);
     return rc;

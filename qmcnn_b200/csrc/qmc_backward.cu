@@ -19,6 +19,8 @@ namespace qmc {
 __global__ void k_repack_params(DevModel m, const float* __restrict__ params, float* __restrict__ padded) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.smem_param_floats) return;
+    params += (size_t)blockIdx.y * m.P;                        // parameter images (qmc_set_image_params)
+    padded += (size_t)blockIdx.y * m.smem_param_floats;
     float v = 0.f;
     for (int l = 0; l < m.D; ++l) {
         const LayerInfo& L = m.layer[l];
@@ -34,10 +36,11 @@ __global__ void k_repack_params(DevModel m, const float* __restrict__ params, fl
     padded[i] = v;
 }
 
-cudaError_t repack_params_to(const qmc_handle* h, const float* flat, float* padded, cudaStream_t st) {
+// `nimg` flat vectors [nimg, P] -> `nimg` padded blocks [nimg, smem_param_floats] in one launch
+cudaError_t repack_params_to(const qmc_handle* h, const float* flat, float* padded, cudaStream_t st, int nimg) {
     const int nthr = 256, nblk = (h->m.smem_param_floats + nthr - 1) / nthr;
     ++g_launches;
-    k_repack_params<<<nblk, nthr, 0, st>>>(h->m, flat, padded);
+    k_repack_params<<<dim3(nblk, nimg), nthr, 0, st>>>(h->m, flat, padded);
     return cudaGetLastError();
 }
 
@@ -61,9 +64,15 @@ __device__ __forceinline__ float2 ctanh_stable(float a, float b) {
 __global__ void __launch_bounds__(kBwdThreads)
 k_backward(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins,
            const float2* __restrict__ weights, int N, const float* __restrict__ cache_all,
-           float* __restrict__ gscratch, float* __restrict__ partial, int gplane_floats) {
+           float* __restrict__ gscratch, float* __restrict__ partial, int gplane_floats, ImageStrides is) {
     extern __shared__ float4 smem4[];
     float* sp = reinterpret_cast<float*>(smem4);
+    // symmetry images (blockIdx.y): own parameter block, cache, per-sample weights, scratch and partial sums
+    params += (size_t)blockIdx.y * is.params;
+    cache_all += (size_t)blockIdx.y * is.cache;
+    weights += (size_t)blockIdx.y * N;
+    gscratch += (size_t)blockIdx.y * gridDim.x * 2 * gplane_floats;
+    partial += (size_t)blockIdx.y * gridDim.x * m.P;
     float* acc = sp + m.smem_param_floats;            // P floats, caller's flat order
     load_params_to_smem(m, params, sp);
     for (int i = threadIdx.x; i < m.P; i += blockDim.x) acc[i] = 0.f;
@@ -195,9 +204,13 @@ constexpr int kBwdSmemThreads = 576;      // = 9 taps x 16 C_in x 4 channel grou
 __global__ void __launch_bounds__(kBwdSmemThreads, 1)
 k_backward_smem(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins,
                 const float2* __restrict__ weights, int N, const float* __restrict__ cache_all,
-                float* __restrict__ partial, int plane_floats) {
+                float* __restrict__ partial, int plane_floats, ImageStrides is) {
     extern __shared__ float4 smem4[];
     float* sp = reinterpret_cast<float*>(smem4);
+    params += (size_t)blockIdx.y * is.params;                  // symmetry images, as in k_backward
+    cache_all += (size_t)blockIdx.y * is.cache;
+    weights += (size_t)blockIdx.y * N;
+    partial += (size_t)blockIdx.y * gridDim.x * m.P;
     float* acc = sp + m.smem_param_floats;                  // P floats, caller's flat order
     float* A = acc + round_up4(m.P);                        // input plane of the current layer
     float* G = A + plane_floats;                            // cotangent of the current layer's output
@@ -354,9 +367,41 @@ __global__ void k_backward_reduce(const float* __restrict__ partial, int nparts,
                                   float* __restrict__ grad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    partial += (size_t)blockIdx.y * nparts * P;                // image blockIdx.y -> grad[image][P]
     float s = 0.f;
     for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * P + i];
-    grad[i] += s;
+    grad[(size_t)blockIdx.y * P + i] += s;
+}
+
+// per-image sample weights of the symmetrised gradient: d/dp sum_n Re[w_n conj(log psi_sym,n)] =
+// sum_g sum_n Re[(w_n conj(p_gn)) conj(d log psi_gn / dp)], p_g = psi_g / sum_h psi_h from the caches' per-site factor
+// planes (differences to image 0 first, in double - k_energy_finish_sym's weights)
+__global__ void k_sym_weights(DevModel m, int nsym, int N, const float* __restrict__ caches,
+                              const float2* __restrict__ w, float2* __restrict__ wimg) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const size_t cimg = (size_t)N * m.cache_floats;
+    const float* c0 = caches + (size_t)s * m.cache_floats;
+    double wr[8], wi[8], sr = 0, si = 0;
+    for (int g = 0; g < nsym; ++g) {
+        const float* cg = c0 + g * cimg;
+        double dre = 0, dim = 0;
+        if (g > 0)
+            for (int i = 0; i < m.n; ++i) {
+                dre += (double)cg[m.fre_off + i] - (double)c0[m.fre_off + i];
+                dim += (double)cg[m.fim_off + i] - (double)c0[m.fim_off + i];
+            }
+        const double a = exp(dre);
+        wr[g] = a * cos(dim); wi[g] = a * sin(dim);
+        sr += wr[g]; si += wi[g];
+    }
+    const double den = sr * sr + si * si;
+    const float2 ws = w[s];
+    for (int g = 0; g < nsym; ++g) {
+        const double pr = (wr[g] * sr + wi[g] * si) / den, pi = (wi[g] * sr - wr[g] * si) / den;   // p_g
+        // w * conj(p_g)
+        wimg[(size_t)g * N + s] = make_float2((float)(ws.x * pr + ws.y * pi), (float)(ws.y * pr - ws.x * pi));
+    }
 }
 
 static int gplane(const DevModel& m);
@@ -383,31 +428,55 @@ static int gplane(const DevModel& m) {
 }
 
 size_t backward_workspace_floats(const qmc_handle* h, int N) {
-    const DevModel& m = h->m;
-    const size_t ctas = backward_ctas(h, N);
-    return (size_t)N * m.cache_floats + ctas * 2 * gplane(m) + ctas * round4(m.P);
+    return backward_images_workspace_floats(h, 1, N);
 }
 
-cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const float* weights, int N,
-                            float* workspace, float* grad, cudaStream_t st, std::string& err) {
+static int backward_image_ctas(const qmc_handle* h, int nimg, int N) {
+    int c = backward_ctas(h, N);
+    if (nimg > 1) { c = c / nimg; if (c < 1) c = 1; }          // the images share the SMs
+    return c;
+}
+
+size_t backward_images_workspace_floats(const qmc_handle* h, int nimg, int N) {
+    const DevModel& m = h->m;
+    const size_t ctas = (size_t)backward_image_ctas(h, nimg, N) * nimg;
+    return (size_t)nimg * N * m.cache_floats + ctas * 2 * gplane(m) + ctas * round4(m.P) + (nimg > 1 ? (size_t)nimg * N * 2 : 0);
+}
+
+// gradient for `nimg` parameter images in one launch sequence: grad [nimg, P] (+=).  nimg == 1: weights [N] are the
+// per-sample cotangents; nimg > 1 (symmetry average): weights [N] are those of log psi_sym and the per-image ones
+// are formed by k_sym_weights
+cudaError_t launch_backward_images(const qmc_handle* h, int nimg, const float* blocks, const int8_t* spins,
+                                   const float* weights, int N, float* workspace, float* grad, cudaStream_t st,
+                                   std::string& err) {
     const DevModel& m = h->m;
     float* cache = workspace;
-    const int ctas = backward_ctas(h, N);
-    float* gscratch = workspace + (size_t)N * m.cache_floats;
-    float* partial = gscratch + (size_t)ctas * 2 * gplane(m);
-    cudaError_t e = launch_forward(h, spins, N, cache, nullptr, nullptr, st, err);
+    const int ctas = backward_image_ctas(h, nimg, N);
+    float* gscratch = workspace + (size_t)nimg * N * m.cache_floats;
+    float* partial = gscratch + (size_t)ctas * nimg * 2 * gplane(m);
+    float* wimg = partial + (size_t)ctas * nimg * round4(m.P);
+    cudaError_t e = launch_forward_images(h, nimg, blocks, spins, N, cache, nullptr, nullptr, st, err);
     if (e != cudaSuccess) return e;
+    const float2* w2 = reinterpret_cast<const float2*>(weights);
+    if (nimg > 1) {
+        if (nimg > 8) { err = "backward: at most 8 images"; return cudaErrorInvalidValue; }
+        ++g_launches;
+        k_sym_weights<<<(N + 127) / 128, 128, 0, st>>>(m, nimg, N, cache, w2, reinterpret_cast<float2*>(wimg));
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        w2 = reinterpret_cast<const float2*>(wimg);
+    }
+    const ImageStrides is{(size_t)m.smem_param_floats, (size_t)N * m.cache_floats};
     if (const size_t sb = backward_smem_bytes(h)) {
         int c = 1;
         for (int l = 0; l < m.D; ++l) c = c > m.layer[l].coutp ? c : m.layer[l].coutp;
         e = cudaFuncSetAttribute(k_backward_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
         if (e != cudaSuccess) return e;
         g_launches += 2;
-        k_backward_smem<<<ctas, kBwdSmemThreads, sb, st>>>(m, h->d_params, spins, reinterpret_cast<const float2*>(weights),
-                                                         N, cache, partial, round4(m.n * c));
+        k_backward_smem<<<dim3(ctas, nimg), kBwdSmemThreads, sb, st>>>(m, blocks, spins, w2, N, cache, partial,
+                                                                     round4(m.n * c), is);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        k_backward_reduce<<<(m.P + 127) / 128, 128, 0, st>>>(partial, ctas, m.P, grad);
+        k_backward_reduce<<<dim3((m.P + 127) / 128, nimg), 128, 0, st>>>(partial, ctas, m.P, grad);
         return cudaGetLastError();
     }
     const size_t smem = (size_t)(m.smem_param_floats + round4(m.P)) * 4;
@@ -415,13 +484,16 @@ cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const floa
     e = cudaFuncSetAttribute(k_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     g_launches += 2;
-    k_backward<<<ctas, kBwdThreads, smem, st>>>(m, h->d_params, spins,
-                                               reinterpret_cast<const float2*>(weights), N, cache,
-                                               gscratch, partial, gplane(m));
+    k_backward<<<dim3(ctas, nimg), kBwdThreads, smem, st>>>(m, blocks, spins, w2, N, cache, gscratch, partial, gplane(m), is);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_backward_reduce<<<(m.P + 127) / 128, 128, 0, st>>>(partial, ctas, m.P, grad);
+    k_backward_reduce<<<dim3((m.P + 127) / 128, nimg), 128, 0, st>>>(partial, ctas, m.P, grad);
     return cudaGetLastError();
+}
+
+cudaError_t launch_backward(const qmc_handle* h, const int8_t* spins, const float* weights, int N,
+                            float* workspace, float* grad, cudaStream_t st, std::string& err) {
+    return launch_backward_images(h, 1, h->d_params_padded, spins, weights, N, workspace, grad, st, err);
 }
 
 } // namespace qmc

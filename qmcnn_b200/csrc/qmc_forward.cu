@@ -17,9 +17,14 @@ constexpr int kFwdBlock = 8;   // output block side per warp task
 __global__ void __launch_bounds__(256, 1)
 k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
           float* __restrict__ cache_all, float2* __restrict__ factors, float2* __restrict__ logpsi,
-          int buf_in_floats, int buf_out_floats, int allow_tiled) {
+          int buf_in_floats, int buf_out_floats, int allow_tiled, ImageStrides is) {
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
+    // symmetry images (blockIdx.y): own parameter block, cache and outputs, the same spins
+    params += (size_t)blockIdx.y * is.params;
+    cache_all += (size_t)blockIdx.y * is.cache;
+    if (factors) factors += (size_t)blockIdx.y * N * m.n;
+    if (logpsi) logpsi += (size_t)blockIdx.y * N;
     // broadcast from lane 0 so the compiler knows the warp index (and everything derived from it:
     // chain, task, loop bounds) is warp-uniform and may use the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -113,6 +118,13 @@ k_forward(DevModel m, const float* __restrict__ params, const int8_t* __restrict
 
 cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
                            float* factors, float* logpsi, cudaStream_t st, std::string& err) {
+    return launch_forward_images(h, 1, h->d_params_padded, spins, N, cache, factors, logpsi, st, err);
+}
+
+// the forward of `nimg` parameter images (qmc_set_image_params) of the same samples in ONE launch:
+// caches [nimg, N, cache_floats], factors [nimg, N, n], logpsi [nimg, N]
+cudaError_t launch_forward_images(const qmc_handle* h, int nimg, const float* padded_blocks, const int8_t* spins, int N,
+                                  float* cache, float* factors, float* logpsi, cudaStream_t st, std::string& err) {
     const DevModel& m = h->m;
     const int p = m.p, side = kFwdBlock + 2 * p;
     int bin = side * side, bout = 0;
@@ -135,11 +147,49 @@ cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, floa
     }
     cudaError_t e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int grid = N < h->num_sms * 4 ? N : h->num_sms * 4;
+    const int per_img = (h->num_sms * 4 + nimg - 1) / nimg;
+    int grid = N < per_img ? N : per_img;
     ++g_launches;
-    k_forward<<<grid, warps * 32, smem, st>>>(m, h->d_params, spins, N, cache,
+    const ImageStrides is{(size_t)m.smem_param_floats, (size_t)N * m.cache_floats};
+    k_forward<<<dim3(grid, nimg), warps * 32, smem, st>>>(m, padded_blocks, spins, N, cache,
                                              reinterpret_cast<float2*>(factors),
-                                             reinterpret_cast<float2*>(logpsi), bin, bout, h->allow_tiled ? 1 : 0);
+                                             reinterpret_cast<float2*>(logpsi), bin, bout, h->allow_tiled ? 1 : 0, is);
+    return cudaGetLastError();
+}
+
+// log psi_g - log psi_0 of every image (double; per-site factor differences first, so that the ~1e2-sized totals
+// never meet in fp32) and log psi_sym = log psi_0 + log mean_g exp(log psi_g - log psi_0), from the images' caches
+__global__ void k_sym_logrel(DevModel m, int nsym, int N, const float* __restrict__ caches, double* __restrict__ log_rel,
+                             float2* __restrict__ logpsi_sym) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const size_t cimg = (size_t)N * m.cache_floats;
+    const float* c0 = caches + (size_t)s * m.cache_floats;
+    double l0r = 0, l0i = 0, sr = 0, si = 0;
+    if (logpsi_sym)
+        for (int i = 0; i < m.n; ++i) { l0r += (double)c0[m.fre_off + i]; l0i += (double)c0[m.fim_off + i]; }
+    for (int g = 0; g < nsym; ++g) {
+        const float* cg = c0 + g * cimg;
+        double dre = 0, dim = 0;
+        if (g > 0)
+            for (int i = 0; i < m.n; ++i) {
+                dre += (double)cg[m.fre_off + i] - (double)c0[m.fre_off + i];
+                dim += (double)cg[m.fim_off + i] - (double)c0[m.fim_off + i];
+            }
+        if (log_rel) { log_rel[((size_t)s * nsym + g) * 2] = dre; log_rel[((size_t)s * nsym + g) * 2 + 1] = dim; }
+        const double a = exp(dre);
+        sr += a * cos(dim); si += a * sin(dim);
+    }
+    if (logpsi_sym) {
+        sr /= nsym; si /= nsym;
+        logpsi_sym[s] = make_float2((float)(l0r + 0.5 * log(sr * sr + si * si)), (float)(l0i + atan2(si, sr)));
+    }
+}
+
+cudaError_t launch_sym_logrel(const qmc_handle* h, int nsym, int N, const float* caches, double* log_rel,
+                              float* logpsi_sym, cudaStream_t st) {
+    ++g_launches;
+    k_sym_logrel<<<(N + 127) / 128, 128, 0, st>>>(h->m, nsym, N, caches, log_rel, reinterpret_cast<float2*>(logpsi_sym));
     return cudaGetLastError();
 }
 

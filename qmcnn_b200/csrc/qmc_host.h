@@ -124,10 +124,15 @@ struct SweepArgs {
     unsigned long long* n_accept;
 };
 
+// symmetry images as an extra grid dimension (blockIdx.y): float strides of the parameter blocks and the caches
+struct ImageStrides { size_t params, cache; };
+
 // launchers (each in its own .cu); return cudaError_t of the launch
 cudaError_t repack_params(const qmc_handle* h, cudaStream_t st);
 cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, float* cache,
                            float* factors, float* logpsi, cudaStream_t st, std::string& err);
+cudaError_t launch_forward_images(const qmc_handle* h, int nimg, const float* padded_blocks, const int8_t* spins, int N,
+                                  float* cache, float* factors, float* logpsi, cudaStream_t st, std::string& err);
 cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
 struct IpLaunch { IpPlan ip; int warps, grid; size_t smem; bool ok; };
 IpPlan ip_plan(const qmc_handle* h);
@@ -140,7 +145,7 @@ cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, co
 cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, double* drel, cudaStream_t st,
                              std::string& err);
 int sweep_sym_slots(const qmc_handle* h, int S, int num_flips, int nsym, EvalPlan* plan, WarpGrid* grid);
-cudaError_t repack_params_to(const qmc_handle* h, const float* flat, float* padded, cudaStream_t st);
+cudaError_t repack_params_to(const qmc_handle* h, const float* flat, float* padded, cudaStream_t st, int nimg = 1);
 cudaError_t launch_energy(const qmc_handle* h, int hamiltonian, float field_h, const int8_t* spins,
                           int N, float* workspace, float* e_loc, double* moments, cudaStream_t st,
                           std::string& err);
@@ -153,5 +158,15 @@ cudaError_t launch_energy_finish(const qmc_handle* h, const int8_t* spins, int N
                                  cudaStream_t st);
 int energy_chunks(const qmc_handle* h);
 size_t backward_workspace_floats(const qmc_handle* h, int N);
+// symmetry images (qmc_set_image_params): every image in the same launches (image = blockIdx.y)
+size_t backward_images_workspace_floats(const qmc_handle* h, int nimg, int N);
+cudaError_t launch_backward_images(const qmc_handle* h, int nimg, const float* blocks, const int8_t* spins,
+                                   const float* weights, int N, float* workspace, float* grad, cudaStream_t st,
+                                   std::string& err);
+size_t energy_sym_workspace_floats(const qmc_handle* h, int nsym, int N);
+cudaError_t launch_energy_sym(const qmc_handle* h, int nsym, int hamiltonian, float field_h, const int8_t* spins, int N,
+                              float* workspace, float* e_loc, double* moments, cudaStream_t st, std::string& err);
+cudaError_t launch_sym_logrel(const qmc_handle* h, int nsym, int N, const float* caches, double* log_rel,
+                              float* logpsi_sym, cudaStream_t st);
 
 } // namespace qmc

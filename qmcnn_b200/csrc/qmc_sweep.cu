@@ -156,7 +156,7 @@ cudaError_t QMC_CAT(launch_sweep_w, QMC_MAXW)(const qmc_handle* h, const SweepAr
     cudaError_t e = cudaFuncSetAttribute(K_SWEEP, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     ++g_launches;
-    K_SWEEP<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params, a, pl, h->allow_tiled ? 1 : 0);
+    K_SWEEP<<<g.grid, g.warps * 32, g.smem, st>>>(h->m, h->d_params_padded, a, pl, h->allow_tiled ? 1 : 0);
     return cudaGetLastError();
 }
 

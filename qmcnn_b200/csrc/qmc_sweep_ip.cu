@@ -358,7 +358,7 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
         const long long left = sl.n_tasks - sl.task0;
         const long long ctas = ((left < slots ? left : slots) + L.warps - 1) / L.warps;
         ++g_launches;
-        kern<<<(int)ctas, L.warps * 32, L.smem, st>>>(h->m, h->d_params, a, L.ip, sl, h->d_ip_tab);
+        kern<<<(int)ctas, L.warps * 32, L.smem, st>>>(h->m, h->d_params_padded, a, L.ip, sl, h->d_ip_tab);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -448,7 +448,7 @@ cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, co
     cudaError_t e = cudaFuncSetAttribute(k_energy_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     ++g_launches;
-    k_energy_ip<<<grid, w * 32, smem, st>>>(h->m, h->d_params, spins, N, cache, partial, nchunks, ip,
+    k_energy_ip<<<grid, w * 32, smem, st>>>(h->m, h->d_params_padded, spins, N, cache, partial, nchunks, ip,
                                             h->ip_group > 0 ? h->ip_group : 4, h->d_ip_tab);
     return cudaGetLastError();
 }

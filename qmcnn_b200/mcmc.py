@@ -38,8 +38,7 @@ def _is_sym(model):
 def _local_energy(model, states, system_shape, hamiltonian, h_field, moments=None):
     if _is_sym(model):     # E_loc[psi_sym] = sum_g p_g E_loc[psi_g]
         shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
-        fn = lambda im, st, system_shape: _local_energy(im, st, system_shape, hamiltonian, h_field)
-        return model.local_energy(fn, states, shape)
+        return model.local_energy(hamiltonian, h_field, states, shape, moments)
     if getattr(model, "n_dims", 2) != 2:
         # 1-D / 3-D lattices: the generic path (one full network evaluation per connected configuration)
         shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
@@ -116,7 +115,7 @@ def logpsi_gradient(model, states, weights, system_shape=None, out=None):
     With w_n = (E_n - mean E)/N this is d loss_op / d p (``mcmc_tf.py:172-177``)."""
     if _is_sym(model):
         shape = tuple(SYSTEM_SHAPE if system_shape is None else system_shape)
-        g = model.gradient(lambda im, st, w, sh: logpsi_gradient(im, st, w, sh), states, weights, shape)
+        g = model.gradient(states, weights, shape)
         if out is not None:
             out.add_(g)
             return out

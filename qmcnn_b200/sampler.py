@@ -171,17 +171,9 @@ class Sampler(object):
             self._samples.zero_()
             return
         if self._sym:
-            # caches of the 8 images + relative log amplitudes from per-site factor differences
-            S, cf = self.num_samplers, self._h.cache_floats
-            facs = []
-            for g, im in enumerate(self.model.images()):
-                f, _, _ = im.forward_unpadded(self._spins, self.system_shape, want_factors=True,
-                                              cache=self._cache[g * S * cf:(g + 1) * S * cf])
-                facs.append(f.to(torch.complex128))
-            for g in range(len(facs)):
-                d = (facs[g] - facs[0]).sum(1)
-                self._log_rel[:, g, 0] = d.real
-                self._log_rel[:, g, 1] = d.imag
+            # caches of the 8 images + relative log amplitudes (per-site factor differences, double): 2 launches
+            self.model.forward_images(self._spins, self.system_shape, caches=self._cache, log_rel=self._log_rel,
+                                      want_logpsi=False)
         else:
             self.model.forward_unpadded(self._spins, self.system_shape, want_factors=False,
                                         cache=self._cache)

@@ -143,6 +143,75 @@ class SymmetrizedModel(object):
     def handle(self, system_shape):
         return self.base.handle(system_shape)
 
+    # ---- the images as an extra grid dimension of the same launches (qmc_*_sym) -------------
+    def _bind(self, system_shape):
+        """Handle with the current image parameter blocks uploaded (qmc_set_image_params)."""
+        h = self.base.handle(system_shape)
+        imgs = self.sync().contiguous()
+        _lib.check(h.ptr, _lib.load().qmc_set_image_params(h.ptr, self.NSYM, imgs.data_ptr(), _stream_ptr(self.device)),
+                   "qmc_set_image_params")
+        return h
+
+    def _states(self, states, h):
+        st = torch.as_tensor(states, device=self.device).reshape(-1, h.n)
+        if st.dtype != torch.int8:
+            st = st.to(torch.int8)
+        return st.contiguous()
+
+    def forward_images(self, spins, system_shape, caches=None, log_rel=None, want_logpsi=True):
+        """One launch for the 8 forwards + one for the combination: fills ``caches`` [8, N, cache_floats]
+        and ``log_rel`` [N, 8, 2] (float64, log psi_g - log psi_0) when given; returns log psi_sym (N,)."""
+        h = self._bind(system_shape)
+        st = self._states(spins, h)
+        N = st.shape[0]
+        if caches is None:
+            caches = torch.empty(self.NSYM * N * h.cache_floats, dtype=torch.float32, device=self.device)
+        out = torch.empty(N, dtype=torch.complex64, device=self.device) if want_logpsi else None
+        _lib.check(h.ptr, _lib.load().qmc_logpsi_forward_sym(
+            h.ptr, self.NSYM, st.data_ptr(), N, caches.data_ptr(),
+            log_rel.data_ptr() if log_rel is not None else None,
+            out.data_ptr() if want_logpsi else None, _stream_ptr(self.device)), "qmc_logpsi_forward_sym")
+        return out
+
+    def log_psi(self, spins, system_shape):
+        """log psi_sym = log((1/8) sum_g psi_g), complex64 (N,)."""
+        return self.forward_images(spins, system_shape)
+
+    def local_energy(self, hamiltonian, h_field, states, system_shape, moments=None):
+        """E_loc[psi_sym] = sum_g p_g E_loc[psi_g] in three launches (forward of all images, connected
+        configurations of all images, combination) - ``qmc_local_energy_sym``."""
+        h = self._bind(system_shape)
+        st = self._states(states, h)
+        N = st.shape[0]
+        out = torch.empty(N, dtype=torch.complex64, device=self.device)
+        if N == 0:
+            return out
+        lib = _lib.load()
+        ws = torch.empty(lib.qmc_sym_energy_workspace_floats(h.ptr, self.NSYM, N), dtype=torch.float32, device=self.device)
+        _lib.check(h.ptr, lib.qmc_local_energy_sym(
+            h.ptr, self.NSYM, hamiltonian, float(h_field), st.data_ptr(), N, ws.data_ptr(), out.data_ptr(),
+            moments.data_ptr() if moments is not None else None, _stream_ptr(self.device)), "qmc_local_energy_sym")
+        return out
+
+    def gradient(self, states, weights, system_shape):
+        """sum_n Re[w_n conj(d log psi_sym,n / dp)] in ``base.flat`` order: the 8 image gradients come out of
+        one launch sequence (``qmc_logpsi_backward_sym``) and are scattered back through the tap permutation."""
+        h = self._bind(system_shape)
+        st = self._states(states, h)
+        N = st.shape[0]
+        out = torch.zeros_like(self.base.flat)
+        if N == 0:
+            return out
+        lib = _lib.load()
+        w = weights.to(torch.complex64).contiguous()
+        gi = torch.zeros((self.NSYM, self.num_params), dtype=torch.float32, device=self.device)
+        ws = torch.empty(lib.qmc_sym_backward_workspace_floats(h.ptr, self.NSYM, N), dtype=torch.float32, device=self.device)
+        _lib.check(h.ptr, lib.qmc_logpsi_backward_sym(h.ptr, self.NSYM, st.data_ptr(), w.data_ptr(), N, ws.data_ptr(),
+                                                      gi.data_ptr(), _stream_ptr(self.device)), "qmc_logpsi_backward_sym")
+        out.index_add_(0, self.index.reshape(-1), gi.reshape(-1))
+        return out
+
+    # ---- image-by-image composition (8 x the plain entry points): the cross-check of the launches above ----
     def log_psi_images(self, spins, system_shape):
         """(8, N) complex64."""
         return torch.stack([im.log_psi(spins, system_shape) for im in self.images()], 0)
@@ -154,20 +223,19 @@ class SymmetrizedModel(object):
         w = torch.exp(z)
         return w / w.sum(0, keepdim=True)
 
-    def log_psi(self, spins, system_shape):
+    def log_psi_composed(self, spins, system_shape):
         logs = self.log_psi_images(spins, system_shape).to(torch.complex128)
         m = logs.real.max(0).values
         return (torch.log(torch.exp(logs - m).mean(0)) + m).to(torch.complex64)
 
-    def local_energy(self, energy_fn, states, system_shape, **kw):
+    def local_energy_composed(self, energy_fn, states, system_shape, **kw):
         """sum_g p_g E_loc[psi_g]; ``energy_fn`` is ising_energy / heisenberg_energy."""
         logs = self.log_psi_images(states, system_shape)
         p = self.image_weights(logs)
         e = torch.stack([energy_fn(im, states, system_shape=system_shape, **kw) for im in self._images], 0)
         return (p * e.to(torch.complex128)).sum(0).to(torch.complex64)
 
-    def gradient(self, grad_fn, states, weights, system_shape):
-        """sum_n Re[w_n conj(d log psi_sym,n / dp)] in ``base.flat`` order."""
+    def gradient_composed(self, grad_fn, states, weights, system_shape):
         logs = self.log_psi_images(states, system_shape)
         p = self.image_weights(logs)
         out = torch.zeros_like(self.base.flat)

@@ -94,3 +94,46 @@ def test_sym_sweep_lockstep(num_flips):
     assert 0.05 < acc.mean() < 0.99
     if num_flips == 2:
         assert acc[2, 1]
+
+
+@pytest.mark.parametrize("kind,L,kw", [("crbm", 10, dict(k=5, alpha=4)), ("dcrbm", 8, dict(k=3, layers=[4, 6, 4]))])
+def test_sym_one_launch_paths_equal_image_composition(kind, L, kw):
+    """north_star (3): the symmetry average is folded into the launches (image = blockIdx.y).  The entry points
+    qmc_logpsi_forward_sym / qmc_local_energy_sym / qmc_logpsi_backward_sym must agree with composing 8 plain calls
+    per image in torch (complex128 softmax), and stay within their launch budgets (2 / 3 / 4 + the parameter repack)."""
+    q, sm, om = _pair(kind, L, 2e-1, 47, **kw)
+    from qmcnn_b200 import _lib
+    lib = _lib.load()
+    shape = (L, L)
+    rng = np.random.default_rng(5)
+    N = 37
+    st = torch.as_tensor((rng.integers(0, 2, (N, L * L)) * 2 - 1).astype(np.int8), device="cuda")
+    w = torch.as_tensor(((rng.standard_normal(N) + 1j * rng.standard_normal(N)) / N).astype(np.complex64), device="cuda")
+
+    def launches(fn):
+        n0 = lib.qmc_launch_count()
+        sm._bind(shape)                                  # the parameter repack launches are not part of the budget
+        n_bind = lib.qmc_launch_count() - n0
+        n0 = lib.qmc_launch_count()
+        out = fn()
+        return out, lib.qmc_launch_count() - n0 - n_bind
+
+    lp, n = launches(lambda: sm.log_psi(st, shape))
+    assert n <= 2, n
+    want = sm.log_psi_composed(st, shape)
+    assert (torch.exp(lp.to(torch.complex128) - want.to(torch.complex128)) - 1).abs().max().item() < 1e-5
+    for ham, fn, kwargs in (("tfim", q.ising_energy, dict(H=0.7)), ("heis", q.heisenberg_energy, {})):
+        if ham == "heis" and om.r + 1 > L:
+            continue
+        e, n = launches(lambda: fn(sm, st, system_shape=shape, **kwargs))
+        assert n <= 3, (ham, n)
+        want = sm.local_energy_composed(fn, st, shape, **kwargs)
+        assert (e - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item()), ham
+    g, n = launches(lambda: q.logpsi_gradient(sm, st, w, shape))
+    assert n <= 4, n
+    want = sm.gradient_composed(lambda im, s_, w_, sh: q.logpsi_gradient(im, s_, w_, sh), st, w, shape)
+    assert (g - want).abs().max().item() < 1e-4 * max(1.0, want.abs().max().item())
+    # moments accumulate in the same call
+    mom = torch.zeros(4, dtype=torch.float64, device="cuda")
+    e = q.ising_energy(sm, st, system_shape=shape, H=0.7, moments=mom)
+    assert mom[0].item() == N and abs(mom[1].item() - e.real.double().sum().item()) < 1e-6 * N
