@@ -270,6 +270,8 @@ def run_cuda(args, cfg, name):
         model = q.DCRBM(cfg["k"], cfg["layers"], 2, device=dev, seed=0)
     params_host = torch.as_tensor(flat_params(cfg, 1234, args.sigma)).pin_memory()
     model.set_flat_params(params_host)
+    if args.tuning:       # experiments only (model.tuning -> qmc_model_desc.reserved): "max_warps=8,ip_group=2,flags=0x40"
+        model.tuning = {k: int(v, 0) for k, v in (kv.split("=") for kv in args.tuning.split(","))}
     base_model = model
     if cfg.get("sym"):
         model = q.SymmetrizedModel(model)      # D4 x| T averaged amplitude (8 filter images)
@@ -325,6 +327,17 @@ def run_cuda(args, cfg, name):
     sync()
     clk = clocks.stop() if clocks else None
     gpu_launches = int(lib.qmc_launch_count() - launches0)     # counted by the library itself
+    import ctypes
+    prof = (ctypes.c_ulonglong * 21)()
+    lib.qmc_diag_ip_profile(prof)            # all zero unless the library is a -DQMC_IP_PROFILE=1 variant build
+    if prof[8] and rank == 0:
+        names = ["draw+top barrier", "spin tile+gathers", "layer 0", "layer barriers", "conv loops", "tanh epilogues",
+                 "head", "accept+commit"]
+        print("k_sweep_ip phase cycles per proposal per warp: " +
+              ", ".join("%s %.1fk" % (nm, prof[i] / prof[8] / 1e3) for i, nm in enumerate(names)) +
+              "; total %.1fk" % (sum(prof[:8]) / prof[8] / 1e3) +
+              "; task duration by warp index relative to warp 0: " +
+              " ".join("%.3f" % (prof[9 + w] / max(prof[9], 1)) for w in range(12)), file=sys.stderr)
     elapsed_ms = t_start.elapsed_time(t_end)
     seg = {"sweep": 0.0, "energy": 0.0, "gradient": 0.0}
     for e0, e1, e2, e3 in marks:
@@ -468,6 +481,7 @@ def main():
     ap.add_argument("--ref-its", type=int, default=256)
     ap.add_argument("--ref-energy", type=int, default=4)
     ap.add_argument("--lib", default="", help="A/B measurements: load this build of the library instead of the in-tree one")
+    ap.add_argument("--tuning", default="", help="experiments: model.tuning as key=int pairs, e.g. max_warps=8,ip_group=2")
     ap.add_argument("--sigma", type=float, default=SCALE,
                     help="std of the synthetic parameters (models.py SCALE = 1e-2: acceptance ~ 1; 1e-1: non-trivial)")
     args = ap.parse_args()

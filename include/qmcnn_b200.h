@@ -65,7 +65,9 @@ typedef struct {
                                          decomposition):
                                            [0] QMC_FLAG_* bits
                                            [1] max warps per CTA of the persistent kernels (0 = as many as fit)
-                                           [2] warps per phase group of k_sweep_ip (0 = 4)
+                                           [2] bits 0-7: warps per phase group of k_sweep_ip (0 = 4); bits 8-23: start
+                                               offset between the phase groups in units of 1024 cycles (0 = 40,
+                                               0xFFFF = none)
                                            [3] max chunks per chain of the time-sliced sweep (0 = 64) */
 } qmc_model_desc;
 
@@ -235,6 +237,11 @@ int qmc_nd_logpsi_backward(const qmc_nd_desc* d, int device, const float* params
 int qmc_diag_peaks(int device, double* fp32_tflops /*host*/, double* mufu_gops /*host*/);
 /* same, plus the packed fma.rn.f32x2 (FFMA2) rate in TFLOP/s */
 int qmc_diag_peaks2(int device, double* fp32_tflops, double* ffma2_tflops, double* mufu_gops);
+/* Phase timers of k_sweep_ip since the last call - only in builds with -DQMC_IP_PROFILE=1 (scripts/build_variant.sh),
+ * all zero otherwise.  out[0..7]: clock64 cycles summed over warps for draw + top barrier, spin tile + frame gathers,
+ * layer 0, layer barriers, conv accumulation loops, tanh epilogues, head, accept + commit; out[8]: proposals;
+ * out[9 + w]: task duration (cycles) of warp w of a CTA, summed over CTAs and launches. */
+int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/);
 
 /* number of CUDA kernels this library has launched in this process (graph replays count
  * their kernel nodes) */

@@ -92,6 +92,7 @@ SIGNATURES = {
     "qmc_nd_logpsi_backward": (_i, [C.POINTER(NdDesc), _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "qmc_diag_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_diag_peaks2": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "qmc_diag_ip_profile": (_i, [C.POINTER(C.c_ulonglong)]),
     "qmc_launch_count": (C.c_ulonglong, []),
     "qmc_version": (C.c_char_p, []),
 }
@@ -124,7 +125,7 @@ class Handle(object):
     """One qmc_handle: a model on one lattice shape on one device."""
 
     def __init__(self, kind, k, channels, Ly, Lx, device, tuning=None):
-        """``tuning``: dict with any of flags (FLAG_* bits), max_warps, ip_group, ip_chunks -> desc.reserved."""
+        """``tuning``: dict with any of flags (FLAG_* bits), max_warps, ip_group, ip_chunks, ip_stagger -> desc.reserved."""
         lib = load()
         d = ModelDesc()
         d.kind, d.k, d.n_layers, d.Ly, d.Lx = kind, k, len(channels), Ly, Lx
@@ -133,6 +134,9 @@ class Handle(object):
         tuning = dict(tuning or {})
         for i, key in enumerate(("flags", "max_warps", "ip_group", "ip_chunks")):
             d.reserved[i] = int(tuning.pop(key, 0))
+        if "ip_stagger" in tuning:      # start offset between phase groups, x 1024 cycles (0 = none; absent = default)
+            st = int(tuning.pop("ip_stagger"))
+            d.reserved[2] = (d.reserved[2] & 0xFF) | ((st if st > 0 else 0xFFFF) << 8)
         if tuning:
             raise QmcError("unknown tuning keys: %s" % sorted(tuning))
         self._h = _vp()

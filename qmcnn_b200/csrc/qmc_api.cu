@@ -129,7 +129,11 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     h->energy_path = (flags & QMC_FLAG_ENERGY_CLASSIC) ? 1 : (flags & QMC_FLAG_ENERGY_INPLACE) ? 2 : 0;
     h->backward_generic = (flags & QMC_FLAG_BACKWARD_GENERIC) != 0;
     h->max_warps_override = desc->reserved[1] > 0 ? desc->reserved[1] : 0;
-    h->ip_group = desc->reserved[2] > 0 ? desc->reserved[2] : 4;
+    h->ip_group = (desc->reserved[2] & 0xFF) > 0 ? (desc->reserved[2] & 0xFF) : 4;
+    {   // phase-group start offset of k_sweep_ip in units of 1024 cycles: 0 = default (40), 0xFFFF = none
+        const int st = (desc->reserved[2] >> 8) & 0xFFFF;
+        h->ip_stagger = st == 0 ? 40 : st == 0xFFFF ? 0 : st;
+    }
     h->ip_chunks = desc->reserved[3] > 0 ? desc->reserved[3] : 64;
     e = cudaMalloc(&h->d_params, sizeof(float) * (size_t)m.P);
     if (e == cudaSuccess) e = cudaMemset(h->d_params, 0, sizeof(float) * (size_t)m.P);

@@ -24,6 +24,7 @@ struct qmc_handle {
     int ip_group = 4;            // reserved[2]: warps per phase group of k_sweep_ip<3>
     int ip_sync = 3;             // 0 (QMC_FLAG_IP_FREE_RUNNING): k_sweep_ip's warps run free; 3: a named barrier per
                                  // layer within each phase group of ip_group warps
+    int ip_stagger = 40;         // reserved[2] >> 8: start offset between the phase groups of k_sweep_ip (x 1024 cycles)
     int ip_chunks = 64;          // reserved[3]: at most this many chunks per chain of the time-sliced sweep
     bool ip_cf = true;           // !QMC_FLAG_IP_ROWMAJOR_SITES: conflict-free site tables for the in-place evaluator
     unsigned short* d_ip_tab = nullptr;   // device image of the tables (ip_upload_tables), or nullptr

@@ -6,6 +6,31 @@
 
 namespace qmc {
 
+// Phase timers (variant builds only: scripts/build_variant.sh out.so "-DQMC_IP_PROFILE=1", read with
+// qmc_diag_ip_profile): clock64 at the phase boundaries of a proposal, summed per warp, added to a global table at
+// the end of the kernel.  Phases: 0 draw + barrier wait at the top of the proposal, 1 spin tile + frame gathers,
+// 2 layer 0, 3 barrier waits in front of the layers, 4 conv accumulation loops, 5 tanh epilogues + frame waits,
+// 6 head, 7 accept + commit + sample write-out.
+#ifndef QMC_IP_PROFILE
+#define QMC_IP_PROFILE 0
+#endif
+constexpr int kIpProfPhases = 8;
+#if QMC_IP_PROFILE
+__shared__ int s_ip_conv[4];          // warps of scheduler (warp & 3) that are inside a conv accumulation loop right now
+__device__ unsigned long long g_ip_conc[4];   // histogram: tap iterations that saw 1, 2, 3, 4+ warps of the scheduler in conv
+#endif
+struct IpProf {
+#if QMC_IP_PROFILE
+    long long last, acc[kIpProfPhases];
+
+    __device__ __forceinline__ void start() { last = clock64(); }
+    __device__ __forceinline__ void mark(int i) { const long long now = clock64(); acc[i] += now - last; last = now; }
+#else
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void mark(int) {}
+#endif
+};
+
 // Out-of-line epilogue pieces.  The kernel runs 12 warps per SM at unrelated program counters and
 // the instruction caches are small (L1.5: 32 KB = 2048 instructions), so code that is executed
 // once per proposal must be compact: 64 inlined tanhf per register tile were 18 KB per tile shape
@@ -90,11 +115,171 @@ __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Split-channel register tile.  conv_region_tiled gives a lane P sites x ALL output channels, so every weight is an
+// all-lane broadcast LDS.128 - two shared-memory wavefronts for 16 bytes - and the conv loops of k_sweep_ip were
+// co-limited by the shared-memory pipe (r01 capture: 10.96k wavefronts per proposal, 5.2k of them weight broadcasts;
+// 4 SMSPs x 10.96k = 75% of the SM's wavefront slots at the measured rate, next to 51% of the FMA pipe).
+// scripts/proto/lds_patterns.cu measured what an LDS.128 costs on sm_100: 4 cycles for 32 different addresses, 2 when
+// the 16 lanes of each half-warp ask for <= 8 different 16-byte words in different bank groups AND every aligned quad
+// of lanes holds at most two different addresses (lane & 3 patterns cost 4; lane >> 1, lane & 1 cost 2).
+// So here lane = (site slot, channel part): CS = 2 parts of COUT / 2 channels, slot = lane >> 1, part = lane & 1.
+// A weight load (2 different addresses, interleaved) still costs 2 but now feeds half as many loads per lane; an
+// input load (16 different sites, 8 per half-warp, dealt conflict-free by the site table) costs 2 instead of 4.
+// Per (tap, 4 input channels): 8 x 2 + 2P x 2 wavefronts instead of 16 x 2 + P x 4 (P = sites per lane before): 20 / 24
+// / 28 / 32 instead of 36 / 40 / 44 / 48 for the 5x5 ... 11x11 windows.  The fma chain of an output value is unchanged
+// (bias, taps ascending, input channels ascending), so results stay bit-identical.
+//   tab: entry [j * NS + slot] = (y << 8) | x of the slot's j-th site or 0xFFFF, NS = 32 / CS slots.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef QMC_IP_SPLIT
+#define QMC_IP_SPLIT 2        // 0: one-part tiles (conv_region_tiled); 2: two channel parts; 4: four parts for small windows
+                              // (4 measured: fewer FFMA2, but 3 more tile bodies - no_instructions 5% -> 12%, 16.0 vs 19.8 M/s)
+#endif
+
+template <int K, int CIN, int COUT, int CS, int P, typename OutF, typename MidF>
+__device__ __forceinline__ void conv_region_split(int wbase, int bbase, const float* wsm, const float* tin, int tw,
+                                                  int tarea, int side, int lane, OutF out, MidF mid,
+                                                  const unsigned short* tab) {
+    static_assert(CS == 2 || CS == 4, "channel parts");
+    constexpr int CL = COUT / CS;             // output channels of this lane
+    constexpr int NS = kWarp / CS;            // site slots
+    constexpr int NCG = CIN / 4;
+    static_assert(CIN % 4 == 0 && CL % 4 == 0, "shape");
+    // aligned lane quads hold two slots x two parts (lds_patterns.cu)
+    const int part = CS == 2 ? (lane & 1) : ((lane >> 1) & 3);
+    const int slot = CS == 2 ? (lane >> 1) : ((lane & 1) | ((lane >> 3) << 1));
+    const float4* tin4 = reinterpret_cast<const float4*>(tin);
+    int toff[P];
+    unsigned valid = 0;                       // bit j: site j of this slot is a real output
+    {
+        const unsigned first = tab[slot];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            unsigned pk = tab[j * NS + slot];
+            if (pk != 0xFFFFu) valid |= 1u << j;
+            else pk = first != 0xFFFFu ? first : 0u;       // duplicate work, result discarded below
+            toff[j] = (int)(pk >> 8) * tw + (int)(pk & 255u);
+        }
+    }
+    const int wlane = wbase + part * CL, blane = bbase + part * CL;
+#if QMC_IP_PROFILE
+    const int sched_ = (threadIdx.x >> 5) & 3;
+    int conc_[4] = {0, 0, 0, 0};
+    if (lane == 0) atomicAdd(&s_ip_conv[sched_], 1);
+#endif
+    float2 acc[P][CL / 2];
+#pragma unroll
+    for (int q2 = 0; q2 < CL / 2; ++q2) {
+        const float2 b = *reinterpret_cast<const float2*>(wsm + blane + 2 * q2);
+#pragma unroll
+        for (int j = 0; j < P; ++j) acc[j][q2] = b;
+    }
+#pragma unroll 1
+    for (int d = 0; d < K * K; ++d) {
+#if QMC_IP_PROFILE
+        { const int v_ = *(volatile int*)&s_ip_conv[sched_]; ++conc_[v_ < 1 ? 0 : v_ > 4 ? 3 : v_ - 1]; }
+#endif
+        const int dy = d / K, dx = d - dy * K;
+        const float4* tp = tin4 + dy * tw + dx;
+        const int wrow = wlane + d * CIN * COUT;
+#pragma unroll(kCgUnroll)
+        for (int cg = 0; cg < NCG; ++cg) {
+            float4 in[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) in[j] = tp[cg * tarea + toff[j]];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float2 w[CL / 2];
+#pragma unroll
+                for (int q4 = 0; q4 < CL / 4; ++q4) {
+                    const float4 t = *reinterpret_cast<const float4*>(wsm + wrow + (cg * 4 + c4) * COUT + q4 * 4);
+                    w[q4 * 2] = make_float2(t.x, t.y);
+                    w[q4 * 2 + 1] = make_float2(t.z, t.w);
+                }
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const float v = c4 == 0 ? in[j].x : c4 == 1 ? in[j].y : c4 == 2 ? in[j].z : in[j].w;
+                    const float2 v2 = make_float2(v, v);
+#pragma unroll
+                    for (int q2 = 0; q2 < CL / 2; ++q2) acc[j][q2] = __ffma2_rn(v2, w[q2], acc[j][q2]);
+                }
+            }
+        }
+    }
+#if QMC_IP_PROFILE
+    if (lane == 0) {
+        atomicSub(&s_ip_conv[sched_], 1);
+        for (int i = 0; i < 4; ++i) if (conc_[i]) atomicAdd(&g_ip_conc[i], (unsigned long long)conc_[i]);
+    }
+#endif
+    mid();
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        if (!((valid >> j) & 1u)) continue;
+        const unsigned pk = tab[j * NS + slot];          // re-read: cheaper than P live registers across the loop
+        const int y = (int)(pk >> 8), x = (int)(pk & 255u);
+        const int pos = y * side + x;
+#pragma unroll
+        for (int q4 = 0; q4 < CL / 4; ++q4)
+            out(pos, y, x, part * (CL / 4) + q4,
+                make_float4(acc[j][q4 * 2].x, acc[j][q4 * 2].y, acc[j][q4 * 2 + 1].x, acc[j][q4 * 2 + 1].y));
+    }
+}
+
+// The register tile of a tiled layer of the in-place evaluator: cs channel parts, p sites per lane, ns = 32 / cs site
+// slots (host and device; p == 0: the window does not fit one round, the model is outside the evaluator's coverage)
+struct IpTile { int cs, p, ns; };
+__host__ __device__ inline IpTile ip_tile(int acc, int cout, int npos) {
+    IpTile t;
+#if QMC_IP_SPLIT
+    // 16 output channels, windows up to 9x9: four channel parts x eight site slots (finer rounding of the window:
+    // 56 instead of 64 site slots for 7x7, 88 instead of 96 for 9x9, and half the weight loads); else two parts
+    if (QMC_IP_SPLIT >= 4 && cout == 16 && npos <= 88) {
+        t.cs = 4;
+        t.ns = kWarp / t.cs;
+        const int need = (npos + t.ns - 1) / t.ns;
+        t.p = need <= 4 ? 4 : need <= 7 ? 7 : 11;
+        return t;
+    }
+    t.cs = 2;
+    t.ns = kWarp / t.cs;
+    const int need = (npos + t.ns - 1) / t.ns;
+    t.p = need <= 2 ? 2 : need <= 4 ? 4 : need <= 6 ? 6 : need <= 8 ? 8 : need <= 11 ? 11 : 0;   // instantiated heights
+    if (t.p * (cout / t.cs) > acc) t.p = 0;
+#else
+    t.cs = 1;
+    t.ns = kWarp;
+    const int pmax = acc / cout;
+    t.p = (pmax == 1 || npos <= 32) ? 1 : (pmax == 2 || npos <= 64) ? 2 : (pmax == 3 || npos <= 96) ? (pmax >= 3 ? 3 : 2)
+        : (pmax == 4 || npos <= 128) ? (pmax >= 4 ? 4 : 2) : (pmax < 8 || npos <= 192) ? (pmax >= 6 ? 6 : 4)
+        : (pmax >= 8 ? 8 : 4);
+    if ((npos + t.p - 1) / t.p > kWarp) t.p = 0;
+#endif
+    return t;
+}
+
 template <int K, int CIN, int COUT, int ACC, typename OutF, typename MidF>
 __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const float* wsm, const float* tin,
                                                     int tw, int tarea, int side, int lane, OutF out, MidF mid,
                                                     const unsigned short* tab) {
     const int npos = side * side;
+#if QMC_IP_SPLIT
+    constexpr int CL = COUT / 2;
+    if constexpr (QMC_IP_SPLIT >= 4 && COUT == 16) {
+#define QMC_SPLIT4(PP) conv_region_split<K, CIN, COUT, 4, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab)
+        if (npos <= 4 * 8) return QMC_SPLIT4(4);
+        if (npos <= 7 * 8) return QMC_SPLIT4(7);
+        if (npos <= 11 * 8) return QMC_SPLIT4(11);
+#undef QMC_SPLIT4
+    }
+#define QMC_SPLIT(PP) conv_region_split<K, CIN, COUT, 2, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab)
+    if (npos <= 2 * 16) return QMC_SPLIT(2);
+    if (npos <= 4 * 16) return QMC_SPLIT(4);
+    if (npos <= 6 * 16) return QMC_SPLIT(6);
+    if constexpr (8 * CL <= ACC) { if (npos <= 8 * 16) return QMC_SPLIT(8); }
+    if constexpr (11 * CL <= ACC) return QMC_SPLIT(11);
+#undef QMC_SPLIT
+#else
     constexpr int PMAX = ACC / COUT;
     auto o = [&](int, int pos, int y, int x, int cog, float4 a) { out(pos, y, x, cog, a); };
 #define QMC_TILED(PP) conv_region_tiled<K, CIN, COUT, (PP), 1>(wbase, bbase, wsm, tin, 0, tw, tarea, side, side, lane, o, mid, tab)
@@ -105,17 +290,7 @@ __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const 
     if (PMAX < 8 || npos <= 192) return QMC_TILED(PMAX >= 6 ? 6 : 4);
     return QMC_TILED(PMAX >= 8 ? 8 : 4);
 #undef QMC_TILED
-}
-
-// sites per lane conv_region_pick_ip uses (host mirror, for the single-round check)
-__host__ __device__ inline int ip_sites_per_lane(int acc, int cout, int npos) {
-    const int pmax = acc / cout;
-    if (pmax == 1 || npos <= 32) return 1;
-    if (pmax == 2 || npos <= 64) return 2;
-    if (pmax == 3 || npos <= 96) return pmax >= 3 ? 3 : 2;
-    if (pmax == 4 || npos <= 128) return pmax >= 4 ? 4 : 2;
-    if (pmax < 8 || npos <= 192) return pmax >= 6 ? 6 : 4;
-    return pmax >= 8 ? 8 : 4;
+#endif
 }
 
 // barrier of the warp's phase group: SYNC 2 = the whole CTA; SYNC 1, 3 = the four warps w/4 == g (one per
@@ -130,16 +305,37 @@ __device__ __forceinline__ void ip_barrier(int gid, int gthreads) {
 // SYNC == 2: a CTA barrier in front of every layer, so that all warps of the SM run the same loop
 // body at the same time (instruction-cache locality; every warp of the CTA must call this the same
 // number of times).
-// commit: scatter the staged window of layer l (src: [cog][pos] float4, in shared memory) into the cache plane
+// Staging layout of a layer's window: plane-major [cog][pos] float4 (default), or - QMC_IP_STAGE_SITEMAJOR, measured
+// and not adopted, profiles/r02_summary.md - site-major [pos][slot] with slot = ip_stage_slot(cog), so that the
+// channel groups a warp-wide store of the split-channel tile writes for one site (one per channel part) are adjacent.
+#ifndef QMC_IP_STAGE_SITEMAJOR
+#define QMC_IP_STAGE_SITEMAJOR 0
+#endif
+// float4 index of (site pos, channel group cog) in a layer's staged window
+__host__ __device__ inline int ip_stage_slot(int cog, int ncg, int cs);
+__host__ __device__ inline int ip_stage_index(int pos, int cog, int rarea, int ncg, int cs) {
+#if QMC_IP_STAGE_SITEMAJOR
+    return pos * ncg + ip_stage_slot(cog, ncg, cs);
+#else
+    return cog * rarea + pos;
+#endif
+}
+__host__ __device__ inline int ip_stage_slot(int cog, int ncg, int cs) {
+    // channel groups per part nq = ncg / cs (all powers of two): cog = part * nq + q -> slot = q * cs + part
+    const int lq = ncg >= 4 * cs ? 2 : ncg >= 2 * cs ? 1 : 0;
+    return cs == 1 ? cog : (cog & ((1 << lq) - 1)) * cs + (cog >> lq);
+}
+
+// commit: scatter the staged window of layer l (src: [pos][slot] float4, in shared memory) into the cache plane
 __device__ __forceinline__ void ip_scatter_layer(const DevModel& m, const LayerInfo& L, const float4* src, float* cache,
-                                                 int side, unsigned mg_side, int ry, int rx, int lane) {
+                                                 int side, unsigned mg_side, int ry, int rx, int lane, int cs) {
     const int rarea = side * side, ncg = L.coutp >> 2, n = m.n;
     float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
     const FastDiv dside(mg_side, side);
     for (int pos = lane; pos < rarea; pos += kWarp) {
         const int y = dside.div(pos), x = pos - y * side;
         const int site = wrap1(ry + y, m.Ly) * m.Lx + wrap1(rx + x, m.Lx);
-        for (int cg = 0; cg < ncg; ++cg) plane4[cg * n + site] = src[cg * rarea + pos];
+        for (int cg = 0; cg < ncg; ++cg) plane4[cg * n + site] = src[ip_stage_index(pos, cg, rarea, ncg, cs)];
     }
 }
 
@@ -151,8 +347,8 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                                                   const unsigned* mg, float* arena, float* spt, const int8_t* spins_s,
                                                   const float* __restrict__ cache, float* staging,
                                                   int site_f, int lane, int gid, int gthreads, float& dre,
-                                                  float* dim_out = nullptr, const int* tabo = nullptr,
-                                                  const unsigned short* tab_s = nullptr) {
+                                                  float* dim_out, const int* tabo, const unsigned short* tab_s,
+                                                  IpProf& prof) {
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n, D = m.D;
     const int T = ip.T, TA = ip.tarea, c = ip.c;
     const int y0 = site_f / Lx, x0 = site_f - y0 * Lx;
@@ -176,6 +372,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         ip_gather_frame(arena4, ip, cache + L.act_off, L.coutp >> 2, n, 2 * p, p, mg[1], y0, x0, Ly, Lx, lane);
     }
     __syncwarp();
+    prof.mark(1);
     int stg = 0;
     {   // layer 0 (C_in = 1) reads the spin tile, not the arena
         const LayerInfo& L = m.layer[0];
@@ -185,36 +382,40 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                             [&](int pos, int y, int x, int cog, float4 a) {
                                 a = ip_tanh4(a);
                                 arena4[cog * TA + (y + o0) * T + (x + o0)] = a;
-                                if (SWEEP) stg4[cog * rarea + pos] = a;
+                                if (SWEEP) stg4[ip_stage_index(pos, cog, rarea, L.coutp >> 2, 1)] = a;
                             });
         stg += L.coutp * rarea;
         cp_async_wait_all();
         __syncwarp();
+        prof.mark(2);
     }
     int side = 1 + 2 * p;
     for (int l = 1; l < D; ++l) {
         const LayerInfo& L = m.layer[l];
         const bool last = (l == D - 1);
         if (SYNC >= 2) ip_barrier<SYNC>(gid, gthreads);
+        prof.mark(3);
         const int hn = (l + 1) * p;                  // half-width of this layer's window
         side += 2 * p;
         const int rarea = side * side;
         const float* tin = arena + (size_t)((c - hn - p) * T + (c - hn - p)) * 4;
         const unsigned short* tab = (tabo && tabo[l] >= 0) ? tab_s + tabo[l] : nullptr;   // conflict-free site deal
-        auto sync = [] { __syncwarp(); };
+        auto sync = [&] { __syncwarp(); prof.mark(4); };
         if (!last) {
             const float* plane = cache + L.act_off;
             const int ncg = L.coutp >> 2, o0 = c - hn;
             ip_gather_frame(arena4, ip, plane, ncg, n, hn + p, p, mg[l + 1], y0, x0, Ly, Lx, lane);   // outer: free now
             float4* stg4 = reinterpret_cast<float4*>(staging + stg);
+            const int tcs = ip_tile(ACC, L.cout, rarea).cs;
             auto out = [&](int pos, int y, int x, int cog, float4 a) {
                 a = ip_tanh4(a);
                 arena4[cog * TA + (y + o0) * T + (x + o0)] = a;
-                if (SWEEP) stg4[cog * rarea + pos] = a;
+                if (SWEEP) stg4[ip_stage_index(pos, cog, rarea, ncg, tcs)] = a;
             };
             // all lanes have read the input tile: the inner frame may land now, under the tanh epilogue
             auto mid = [&] {
                 __syncwarp();
+                prof.mark(4);
                 ip_gather_frame(arena4, ip, plane, ncg, n, hn, p, mg[l], y0, x0, Ly, Lx, lane);
             };
             if (L.cin == 16 && L.cout == 16)
@@ -233,8 +434,10 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                 conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
         }
         __syncwarp();
+        prof.mark(5);
     }
     if (SYNC >= 2) ip_barrier<SYNC>(gid, gthreads);
+    prof.mark(3);
     // commit, part 1 (speculative): the staged windows of the first layers start their way from L2 into the
     // free part of the arena now, so that an accepted move finds them in shared memory after the head
     if (SWEEP) {
@@ -279,6 +482,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
     if (!SWEEP) *dim_out = warp_sum(sim);
     dre = warp_sum(sre);
     __syncwarp();
+    prof.mark(6);
 }
 
 } // namespace qmc

@@ -5,6 +5,7 @@
 // instead of 1.75 - the classic kernel issues on only 44% of cycles because each scheduler has
 // fewer than two warps to choose from).  Single-flip proposals of deep k = 3 models whose
 // windows fit one round of the register tile; everything else runs the classic kernel.
+#include <cstdio>
 #include <vector>
 #include "qmc_host.h"
 #include "qmc_ip.cuh"
@@ -19,7 +20,12 @@ constexpr int kIpAcc = 64;            // accumulators per lane
 // ONE task to every warp slot.  A chain's chunks are in different launches (S >= slots), so the
 // stream orders them; every launch is exactly one full wave, so there is no idle tail whatever S
 // is (4096 chains on 148 x 12 slots would otherwise be 2.3 waves = 77% efficiency).
-struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps; };
+struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps, stagger; };
+
+#if QMC_IP_PROFILE
+__device__ unsigned long long g_ip_prof[kIpProfPhases + 1 + 12];  // cycles per phase summed over warps, [8] = proposals,
+                                                                   // [9 + w] = task duration of warp w summed over CTAs
+#endif
 
 // per-CTA words after the parameter block: division magics, site-table offsets, then the site tables (uint16)
 constexpr int kIpCtaWords = 2 * QMC_MAX_LAYERS;
@@ -53,6 +59,9 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
            const unsigned short* __restrict__ tab_g) {
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
+#if QMC_IP_PROFILE
+    if (threadIdx.x < 4) s_ip_conv[threadIdx.x] = 0;
+#endif
     load_params_to_smem(m, params, smem_f);
     const float* sp = smem_f;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -109,7 +118,23 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
         };
         int f_next = 0;
         float u_next = 0.f;
+        // Phase groups start g * stagger cycles apart.  All warps run the same code on equally sized windows, so groups
+        // that start together stay in lockstep: the three warps of a scheduler are then in the conv loops at the same
+        // time (73% of the tap iterations see all three there, profiles/r02_summary.md) and in the latency-bound
+        // epilogue / head / commit at the same time.  An offset de-phases them for the rest of the launch.
+        if (sl.stagger > 0) {
+            const long long t_go = clock64() + (long long)g * sl.stagger;
+            while (clock64() < t_go) __nanosleep(200);
+        }
+        IpProf prof;
+#if QMC_IP_PROFILE
+        for (int i = 0; i < kIpProfPhases; ++i) prof.acc[i] = 0;
+#endif
         draw(it0 < it1 ? it0 : it1 - 1, f_next, u_next);
+        prof.start();
+#if QMC_IP_PROFILE
+        const long long t_task0 = clock64();
+#endif
         for (long long itx = it0; itx < it0 + sl.chunk_len; ++itx) {
             const bool active = has_task && itx < it1;
             if (!SYNC && !active) break;
@@ -121,11 +146,12 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
             float dre;
             cp_async_wait_all();                              // (a rejected move's speculative commit copy)
             ip_barrier<SYNC>(gid, gthreads);
+            prof.mark(0);
             warp_eval_flip_ip<kIpAcc, SYNC>(m, ip, sp, mg, arena, spt, spins_s, cache, staging, f0, lane, gid, gthreads, dre,
-                                            nullptr, tabo, tab_s);
+                                            nullptr, tabo, tab_s, prof);
             const float amp = expf(dre);                      // |exp(z)| = exp(Re z)
             const bool accept = __shfl_sync(0xffffffffu, (int)(amp * amp > u), 0) != 0;   // strict, sampler.py:125
-            if (SYNC && !active) continue;                    // shadow: nothing is written
+            if (SYNC && !active) { prof.mark(7); continue; }  // shadow: nothing is written
             if (accept) {
                 // commit: new hidden activations, new factors, the spin.  The staged windows travel L2 -> shared
                 // memory in bulk (linear cp.async: the first layers went ahead during the head, the rest follow in
@@ -139,7 +165,8 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
                     const LayerInfo& L = m.layer[l];
                     side += 2 * p;
                     ip_scatter_layer(m, L, reinterpret_cast<const float4*>(arena + ip.spec_off + stg), cache, side,
-                                     l ? mg[l - 1] : ip.mg2p1, y0 - (l + 1) * p, x0 - (l + 1) * p, lane);
+                                     l ? mg[l - 1] : ip.mg2p1, y0 - (l + 1) * p, x0 - (l + 1) * p, lane,
+                                     l ? ip_tile(kIpAcc, L.cout, side * side).cs : 1);
                     stg += L.coutp * side * side;
                 }
                 while (l < D - 1) {
@@ -159,7 +186,8 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
                         const LayerInfo& L = m.layer[l];
                         side += 2 * p;
                         ip_scatter_layer(m, L, reinterpret_cast<const float4*>(arena + off), cache, side,
-                                         l ? mg[l - 1] : ip.mg2p1, y0 - (l + 1) * p, x0 - (l + 1) * p, lane);
+                                         l ? mg[l - 1] : ip.mg2p1, y0 - (l + 1) * p, x0 - (l + 1) * p, lane,
+                                         l ? ip_tile(kIpAcc, L.cout, side * side).cs : 1);
                         off += L.coutp * side * side;
                     }
                     stg += fl;
@@ -186,7 +214,15 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
                     for (int i = lane; i < n; i += kWarp) dst[i] = spins_s[i];
                 }
             }
+            prof.mark(7);
         }
+#if QMC_IP_PROFILE
+        if (lane == 0 && has_task) {
+            for (int i = 0; i < kIpProfPhases; ++i) atomicAdd(&g_ip_prof[i], (unsigned long long)prof.acc[i]);
+            atomicAdd(&g_ip_prof[kIpProfPhases], (unsigned long long)(it1 - it0));
+            if (warp < 12) atomicAdd(&g_ip_prof[kIpProfPhases + 1 + warp], (unsigned long long)(clock64() - t_task0));
+        }
+#endif
         if (has_task)
             for (int i = lane; i < n; i += kWarp) gspins[i] = spins_s[i];
         __syncwarp();
@@ -209,8 +245,7 @@ IpPlan ip_plan(const qmc_handle* h) {
             const bool hidden_ok = (L.cin == 16 && L.cout == 16) || (L.cin == 8 && L.cout == 8);
             const bool last_ok = hidden_ok || (L.cin == 16 && L.cout == 8);
             if (l < m.D - 1 ? !hidden_ok : !last_ok) return ip;
-            const int P = ip_sites_per_lane(kIpAcc, L.cout, npos);
-            if ((npos + P - 1) / P > kWarp) return ip;                        // must be ONE round
+            if (ip_tile(kIpAcc, L.cout, npos).p == 0) return ip;              // must be ONE round of the register tile
         }
         if (l < m.D - 1) {
             if (L.coutp > cmax) cmax = L.coutp;
@@ -248,45 +283,48 @@ IpPlan ip_plan(const qmc_handle* h) {
     ip.mg2p = fastdiv_magic(2 * p);
     ip.mg2p1 = fastdiv_magic(2 * p + 1);
     for (int j = 0; j < m.D; ++j) ip.mgW[j] = fastdiv_magic(2 * (j + 2) * p + 1);
-    // site tables of the tiled layers (ip_site_table): P rows of 32 lanes each
+    // site tables of the tiled layers (ip_site_table): p rows of ns site slots each
     int entries = 0;
     for (int l = 0; l < QMC_MAX_LAYERS; ++l) ip.tab_off[l] = -1;
     for (int l = 1; l < m.D; ++l) {
         const int side = 1 + 2 * (l + 1) * p;
         ip.tab_off[l] = entries;
-        entries += ip_sites_per_lane(kIpAcc, m.layer[l].cout, side * side) * kWarp;
+        const IpTile t = ip_tile(kIpAcc, m.layer[l].cout, side * side);
+        entries += t.p * t.ns;
     }
     ip.tab_entries = (entries + 7) & ~7;
     ip.ok = 1;
     return ip;
 }
 
-// Deal the side x side window of layer l to (site j, lane) slots so that the eight lanes of every quarter warp read
-// eight different 16-byte bank groups of the arena (pitch T float4): walk the sites in row-major order and give
-// each quarter the first unassigned sites whose (y * T + x) mod 8 it does not hold yet.  Row-major preference keeps
-// the staging stores of a quarter nearly contiguous.  Lanes >= G = ceil(npos / P) stay idle as before.
-static void ip_site_table(int side, int T, int P, unsigned short* tab) {
+// Deal the side x side window of layer l to (round j, site slot) so that the eight slots the hardware serves together
+// (a quarter warp of the one-part tile; the 16 lanes of a half-warp of the split-channel tile) read eight different
+// 16-byte bank groups of the arena (pitch T float4): walk the sites in row-major order and give each group of eight
+// the first unassigned sites whose (y * T + x) mod 8 it does not hold yet.  Row-major preference keeps the staging
+// stores of a group nearly contiguous.  Slots >= G = ceil(npos / P) stay idle.  conflict_free = false
+// (QMC_FLAG_IP_ROWMAJOR_SITES): plain row-major deal, for the before / after measurement.
+static void ip_site_table(int side, int T, int P, int NS, bool conflict_free, unsigned short* tab) {
     const int npos = side * side, G = (npos + P - 1) / P;
     std::vector<char> taken(npos, 0);
-    for (int i = 0; i < P * kWarp; ++i) tab[i] = 0xFFFF;
+    for (int i = 0; i < P * NS; ++i) tab[i] = 0xFFFF;
     int left = npos;
     for (int j = 0; j < P; ++j)
-        for (int qd = 0; qd < 4; ++qd) {
+        for (int s0 = 0; s0 < NS; s0 += 8) {
             unsigned used = 0;
-            for (int lane = qd * 8; lane < qd * 8 + 8 && lane < G && left > 0; ++lane) {
+            for (int slot = s0; slot < s0 + 8 && slot < NS && slot < G && left > 0; ++slot) {
                 int pick = -1, fallback = -1;
                 for (int pos = 0; pos < npos; ++pos) {
                     if (taken[pos]) continue;
                     if (fallback < 0) fallback = pos;
                     const int y = pos / side, x = pos - y * side;
-                    if (!((used >> ((y * T + x) & 7)) & 1u)) { pick = pos; break; }
+                    if (!conflict_free || !((used >> ((y * T + x) & 7)) & 1u)) { pick = pos; break; }
                 }
-                if (pick < 0) pick = fallback;          // no conflict-free site is left for this quarter
+                if (pick < 0) pick = fallback;          // no conflict-free site is left for this group
                 const int y = pick / side, x = pick - y * side;
                 used |= 1u << ((y * T + x) & 7);
                 taken[pick] = 1;
                 --left;
-                tab[j * kWarp + lane] = (unsigned short)((y << 8) | x);
+                tab[j * NS + slot] = (unsigned short)((y << 8) | x);
             }
         }
 }
@@ -294,13 +332,13 @@ static void ip_site_table(int side, int T, int P, unsigned short* tab) {
 // device image of the site tables of a handle (built once, qmc_create)
 cudaError_t ip_upload_tables(qmc_handle* h) {
     h->d_ip_tab = nullptr;
-    if (!h->ip_cf) return cudaSuccess;
     const IpPlan ip = ip_plan(h);
     if (!ip.ok || ip.tab_entries == 0) return cudaSuccess;
     std::vector<unsigned short> tab(ip.tab_entries, 0xFFFF);
     for (int l = 1; l < h->m.D; ++l) {
         const int side = 1 + 2 * (l + 1) * h->m.p;
-        ip_site_table(side, ip.T, ip_sites_per_lane(kIpAcc, h->m.layer[l].cout, side * side), tab.data() + ip.tab_off[l]);
+        const IpTile t = ip_tile(kIpAcc, h->m.layer[l].cout, side * side);
+        ip_site_table(side, ip.T, t.p, t.ns, h->ip_cf, tab.data() + ip.tab_off[l]);
     }
     cudaError_t e = cudaMalloc(&h->d_ip_tab, tab.size() * sizeof(unsigned short));
     if (e != cudaSuccess) return e;
@@ -352,6 +390,7 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
     IpSlice sl;
     sl.group_warps = h->ip_group > 0 ? h->ip_group : 4;
     sl.chunk_len = (a.n_steps + chunks - 1) / chunks;
+    sl.stagger = sl.chunk_len >= 64 ? h->ip_stagger * 1024 : 0;     // not worth ~40 us on a launch of a few steps
     chunks = (a.n_steps + sl.chunk_len - 1) / sl.chunk_len;
     sl.n_tasks = chunks * a.S;
     for (sl.task0 = 0; sl.task0 < sl.n_tasks; sl.task0 += slots) {
@@ -411,9 +450,10 @@ k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restri
             const bool active = i0 + ii < i1;
             const int i = active ? i0 + ii : i1 - 1;
             float dre, dim, sn, cn;
+            IpProf prof;
             ip_barrier<3>(gid, gthreads);
             warp_eval_flip_ip<kIpAcc, 3, false>(m, ip, sp, mg, arena, spt, spins_s, cache, nullptr, i, lane, gid,
-                                                gthreads, dre, &dim, tabo, tab_s);
+                                                gthreads, dre, &dim, tabo, tab_s, prof);
             if (!active) continue;
             const float amp = expf(dre);
             sincosf(dim, &sn, &cn);
@@ -454,3 +494,23 @@ cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, co
 }
 
 } // namespace qmc
+
+// phase cycles of k_sweep_ip since the last call (QMC_IP_PROFILE builds; zeros otherwise): out[0..7] cycles summed
+// over warps, out[8] proposals, out[9 + w] task duration of warp w of a CTA summed over CTAs and launches
+extern "C" int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/) {
+    for (int i = 0; i < qmc::kIpProfPhases + 13; ++i) out[i] = 0;
+#if QMC_IP_PROFILE
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, qmc::g_ip_prof, sizeof(qmc::g_ip_prof)) != cudaSuccess) return QMC_ERR_CUDA;
+    unsigned long long zero[qmc::kIpProfPhases + 13] = {};
+    if (cudaMemcpyToSymbol(qmc::g_ip_prof, zero, sizeof(zero)) != cudaSuccess) return QMC_ERR_CUDA;
+    unsigned long long conc[4];
+    if (cudaMemcpyFromSymbol(conc, qmc::g_ip_conc, sizeof(conc)) != cudaSuccess) return QMC_ERR_CUDA;
+    if (cudaMemcpyToSymbol(qmc::g_ip_conc, zero, sizeof(conc)) != cudaSuccess) return QMC_ERR_CUDA;
+    const double ct = (double)(conc[0] + conc[1] + conc[2] + conc[3]);
+    if (ct > 0)
+        fprintf(stderr, "k_sweep_ip conv concurrency (tap iterations that saw 1 / 2 / 3 / 4+ warps of their scheduler in a conv "
+                "loop): %.3f %.3f %.3f %.3f\n", conc[0] / ct, conc[1] / ct, conc[2] / ct, conc[3] / ct);
+#endif
+    return QMC_OK;
+}
