@@ -125,6 +125,8 @@ cudaError_t launch_forward(const qmc_handle* h, const int8_t* spins, int N, floa
 // caches [nimg, N, cache_floats], factors [nimg, N, n], logpsi [nimg, N]
 cudaError_t launch_forward_images(const qmc_handle* h, int nimg, const float* padded_blocks, const int8_t* spins, int N,
                                   float* cache, float* factors, float* logpsi, cudaStream_t st, std::string& err) {
+    if (h->d_plane_tab && forward_plane_supported(h))          // the lattice's planes fit in shared memory
+        return launch_forward_plane(h, nimg, padded_blocks, spins, N, cache, factors, logpsi, st);
     const DevModel& m = h->m;
     const int p = m.p, side = kFwdBlock + 2 * p;
     int bin = side * side, bout = 0;

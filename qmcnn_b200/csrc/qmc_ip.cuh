@@ -36,13 +36,13 @@ struct IpProf {
 // once per proposal must be compact: 64 inlined tanhf per register tile were 18 KB per tile shape
 // and the first version of this kernel stalled 34% of its cycles on instruction fetch.  Same
 // library tanhf / log2cosh_c as every other path, so the results stay bit-identical.
-__device__ __noinline__ float4 ip_tanh4(float4 a) {
+static __device__ __noinline__ float4 ip_tanh4(float4 a) {
     a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
     return a;
 }
 
 // sum_c Re log 2cosh(theta_c + i theta_{c+half}) of one site (site_factor<false> without the CRBM term)
-__device__ __noinline__ float ip_site_re(const float* th, int npos, int pos, int half) {
+static __device__ __noinline__ float ip_site_re(const float* th, int npos, int pos, int half) {
     float re = 0.f;
     // four channels at a time: the loads first, then four independent exp / sincos / log chains the
     // scheduler can interleave (one channel per iteration left this latency-bound at ILP 1); the sum
@@ -77,7 +77,7 @@ __device__ __noinline__ float ip_site_re(const float* th, int npos, int pos, int
 
 // (Re, Im) sum_c log 2cosh(theta_c + i theta_{c+half}) of one site: site_factor<true> without the CRBM term,
 // one channel at a time in site_factor's order (the local-energy kernel needs the complex ratio)
-__device__ __noinline__ float2 ip_site_reim(const float* th, int npos, int pos, int half) {
+static __device__ __noinline__ float2 ip_site_reim(const float* th, int npos, int pos, int half) {
     float re = 0.f, im = 0.f;
     for (int c = 0; c < half; ++c) {
         const int c2 = c + half;

@@ -653,3 +653,24 @@ def test_full_size_c5_shapes():
     a, b = outs
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     assert 0 < int(a[0].sum()) < a[0].numel()
+
+
+@pytest.mark.parametrize("layers,shape", [([16, 16, 16, 16, 16, 8], (20, 20)), ([8, 8, 8], (10, 10)), ([16, 16, 8], (9, 11)),
+                                          ([16, 16, 16], (7, 23)), ([8, 8], (3, 3))])
+def test_plane_forward_is_bit_identical_to_blocked_forward(layers, shape):
+    """k_forward_plane (the sample's planes resident in shared memory, split-channel register tile) against k_forward
+    (8 x 8 blocks through per-warp tiles, QMC_FLAG_FORWARD_BLOCKED): the same fma chain per output, so caches, factors
+    and per-image caches agree bit for bit; log psi (a different summation tree over the sites) to fp32 rounding."""
+    from gpu_util import make_pair, rand_states
+    q = _q()
+    s = torch.as_tensor(rand_states(np.random.default_rng(11), 37, shape))
+    outs = []
+    for flags in (0, q.FLAG_FORWARD_BLOCKED):
+        gm, _ = make_pair("dcrbm", shape[0], 1e-1, 79, layers=layers)
+        gm.tuning = dict(flags=flags)
+        zero = torch.zeros(s.shape[0] * gm.handle(shape).cache_floats, dtype=torch.float32, device="cuda")   # (padding words)
+        f, lp, cache = gm.forward_unpadded(s, shape, want_factors=True, want_logpsi=True, cache=zero)
+        outs.append((f.cpu().numpy(), lp.cpu().numpy(), cache.cpu().numpy()))
+    assert np.array_equal(outs[0][0].view(np.float32), outs[1][0].view(np.float32))
+    assert np.array_equal(outs[0][2], outs[1][2])
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 2e-6 * max(1.0, np.abs(outs[1][1]).max())
