@@ -80,7 +80,9 @@ enum {
     QMC_FLAG_ENERGY_INPLACE = 32,   /* TFIM local energy: k_energy_ip whenever covered */
     QMC_FLAG_BACKWARD_GENERIC = 64, /* gradient: k_backward (planes in L2) instead of k_backward_smem */
     QMC_FLAG_IP_ROWMAJOR_SITES = 128, /* in-place evaluator: row-major site order instead of the conflict-free deal */
-    QMC_FLAG_FORWARD_BLOCKED = 256  /* forward: k_forward (8 x 8 blocks through per-warp tiles) instead of k_forward_plane */
+    QMC_FLAG_FORWARD_BLOCKED = 256, /* forward: k_forward (8 x 8 blocks through per-warp tiles) instead of k_forward_plane */
+    QMC_FLAG_BACKWARD_SMEM = 512    /* gradient: the per-sample kernels (k_backward_smem / k_backward) instead of the
+                                       per-layer band kernels (qmc_backward_plane.cu) */
 };
 
 typedef struct qmc_handle qmc_handle;

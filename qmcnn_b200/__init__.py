@@ -10,7 +10,7 @@ nodes; all arithmetic in hand-written CUDA kernels behind the C ABI of
 from ._lib import QmcError, load as load_library, LIB_PATH
 from ._lib import (FLAG_GENERIC_CONV, FLAG_SWEEP_CLASSIC, FLAG_SWEEP_INPLACE, FLAG_IP_FREE_RUNNING,
                    FLAG_ENERGY_CLASSIC, FLAG_ENERGY_INPLACE, FLAG_BACKWARD_GENERIC, FLAG_IP_ROWMAJOR_SITES,
-                   FLAG_FORWARD_BLOCKED)
+                   FLAG_FORWARD_BLOCKED, FLAG_BACKWARD_SMEM)
 from .helpers import (create_index_matrix, scope_op, pad, unpad, all_windows, gather_windows,
                       update_windows, interactions)
 from .models import CRBM, DCRBM

@@ -16,7 +16,7 @@ TFIM, HEISENBERG = 0, 1
 # tuning / cross-check knobs of a handle (include/qmcnn_b200.h: QMC_FLAG_*, qmc_model_desc.reserved)
 FLAG_GENERIC_CONV, FLAG_SWEEP_CLASSIC, FLAG_SWEEP_INPLACE, FLAG_IP_FREE_RUNNING = 1, 2, 4, 8
 FLAG_ENERGY_CLASSIC, FLAG_ENERGY_INPLACE, FLAG_BACKWARD_GENERIC, FLAG_IP_ROWMAJOR_SITES = 16, 32, 64, 128
-FLAG_FORWARD_BLOCKED = 256
+FLAG_FORWARD_BLOCKED, FLAG_BACKWARD_SMEM = 256, 512
 
 
 class QmcError(RuntimeError):

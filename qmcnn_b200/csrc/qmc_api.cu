@@ -129,6 +129,7 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     h->energy_path = (flags & QMC_FLAG_ENERGY_CLASSIC) ? 1 : (flags & QMC_FLAG_ENERGY_INPLACE) ? 2 : 0;
     h->backward_generic = (flags & QMC_FLAG_BACKWARD_GENERIC) != 0;
     h->forward_blocked = (flags & QMC_FLAG_FORWARD_BLOCKED) != 0;
+    h->backward_smem_only = (flags & QMC_FLAG_BACKWARD_SMEM) != 0;
     h->max_warps_override = desc->reserved[1] > 0 ? desc->reserved[1] : 0;
     h->ip_group = (desc->reserved[2] & 0xFF) > 0 ? (desc->reserved[2] & 0xFF) : 4;
     {   // phase-group start offset of k_sweep_ip in units of 1024 cycles: 0 = default (40), 0xFFFF = none
@@ -142,6 +143,7 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     if (e == cudaSuccess) e = cudaMemset(h->d_params_padded, 0, sizeof(float) * (size_t)m.smem_param_floats);
     if (e == cudaSuccess) e = ip_upload_tables(h);
     if (e == cudaSuccess) e = plane_upload_tables(h);
+    if (e == cudaSuccess) e = bwd_plane_upload_tables(h);
     cudaSetDevice(prev);
     if (e != cudaSuccess) { qmc_destroy(h); return cuda_fail(nullptr, e, "cudaMalloc(params)"); }
     if ((size_t)m.smem_param_floats * 4 > h->max_smem) {
@@ -162,6 +164,7 @@ int qmc_destroy(qmc_handle* h) {
     cudaFree(h->d_sym_padded);
     cudaFree(h->d_ip_tab);
     cudaFree(h->d_plane_tab);
+    cudaFree(h->d_bwd_tab);
     cudaSetDevice(prev);
     delete h;
     return QMC_OK;

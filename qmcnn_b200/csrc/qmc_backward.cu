@@ -438,6 +438,7 @@ static int backward_image_ctas(const qmc_handle* h, int nimg, int N) {
 }
 
 size_t backward_images_workspace_floats(const qmc_handle* h, int nimg, int N) {
+    if (h->d_bwd_tab && backward_plane_supported(h)) return backward_plane_workspace_floats(h, nimg, N);
     const DevModel& m = h->m;
     const size_t ctas = (size_t)backward_image_ctas(h, nimg, N) * nimg;
     return (size_t)nimg * N * m.cache_floats + ctas * 2 * gplane(m) + ctas * round4(m.P) + (nimg > 1 ? (size_t)nimg * N * 2 : 0);
@@ -451,6 +452,30 @@ cudaError_t launch_backward_images(const qmc_handle* h, int nimg, const float* b
                                    std::string& err) {
     const DevModel& m = h->m;
     float* cache = workspace;
+    if (h->d_bwd_tab && backward_plane_supported(h)) {
+        // per-layer band kernels: [caches | 2 x cotangent planes | CTA partials | image weights]
+        if (nimg > 8) { err = "backward: at most 8 images"; return cudaErrorInvalidValue; }
+        const int pc = backward_plane_ctas(h, nimg, N);
+        const size_t gfl = (backward_plane_workspace_floats(h, nimg, N) - (size_t)nimg * N * m.cache_floats -
+                            (size_t)pc * nimg * round4(m.P) - (nimg > 1 ? (size_t)nimg * N * 2 : 0));
+        float* gbuf = workspace + (size_t)nimg * N * m.cache_floats;
+        float* part = gbuf + gfl;
+        float* wim = part + (size_t)pc * nimg * round4(m.P);
+        cudaError_t e2 = launch_forward_images(h, nimg, blocks, spins, N, cache, nullptr, nullptr, st, err);
+        if (e2 != cudaSuccess) return e2;
+        const float2* wv = reinterpret_cast<const float2*>(weights);
+        if (nimg > 1) {
+            ++g_launches;
+            k_sym_weights<<<(N + 127) / 128, 128, 0, st>>>(m, nimg, N, cache, wv, reinterpret_cast<float2*>(wim));
+            if ((e2 = cudaGetLastError()) != cudaSuccess) return e2;
+            wv = reinterpret_cast<const float2*>(wim);
+        }
+        e2 = launch_backward_plane(h, nimg, blocks, spins, wv, N, cache, gbuf, part, grad, st);
+        if (e2 != cudaSuccess) return e2;
+        ++g_launches;
+        k_backward_reduce<<<dim3((m.P + 127) / 128, nimg), 128, 0, st>>>(part, pc, m.P, grad);
+        return cudaGetLastError();
+    }
     const int ctas = backward_image_ctas(h, nimg, N);
     float* gscratch = workspace + (size_t)nimg * N * m.cache_floats;
     float* partial = gscratch + (size_t)ctas * nimg * 2 * gplane(m);

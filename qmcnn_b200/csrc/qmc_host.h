@@ -30,6 +30,8 @@ struct qmc_handle {
     unsigned short* d_ip_tab = nullptr;   // device image of the tables (ip_upload_tables), or nullptr
     int energy_path = 0;         // 0 auto, 1 classic persistent (QMC_FLAG_ENERGY_CLASSIC), 2 in-place (QMC_FLAG_ENERGY_INPLACE)
     bool backward_generic = false;   // QMC_FLAG_BACKWARD_GENERIC
+    bool backward_smem_only = false; // QMC_FLAG_BACKWARD_SMEM: k_backward_smem / k_backward instead of the per-layer band kernels
+    unsigned short* d_bwd_tab = nullptr;     // site tables of the band kernels (bwd_plane_upload_tables), or nullptr
     bool forward_blocked = false;    // QMC_FLAG_FORWARD_BLOCKED: k_forward (8 x 8 blocks) instead of k_forward_plane
     unsigned short* d_plane_tab = nullptr;   // site tables of k_forward_plane (plane_upload_tables), or nullptr
 };
@@ -141,6 +143,13 @@ bool forward_plane_supported(const qmc_handle* h);
 cudaError_t plane_upload_tables(qmc_handle* h);
 cudaError_t launch_forward_plane(const qmc_handle* h, int nimg, const float* padded_blocks, const int8_t* spins, int N,
                                  float* cache, float* factors, float* logpsi, cudaStream_t st);
+// qmc_backward_plane.cu: the gradient layer by layer over all samples, row bands resident in shared memory
+bool backward_plane_supported(const qmc_handle* h);
+cudaError_t bwd_plane_upload_tables(qmc_handle* h);
+size_t backward_plane_workspace_floats(const qmc_handle* h, int nimg, int N);
+int backward_plane_ctas(const qmc_handle* h, int nimg, int N);
+cudaError_t launch_backward_plane(const qmc_handle* h, int nimg, const float* blocks, const int8_t* spins, const float2* w,
+                                  int N, const float* cache, float* gbuf, float* partial, float* grad, cudaStream_t st);
 cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t st, std::string& err);
 struct IpLaunch { IpPlan ip; int warps, grid; size_t smem; bool ok; };
 IpPlan ip_plan(const qmc_handle* h);

@@ -544,12 +544,44 @@ def test_shared_memory_backward_matches_generic_and_oracle(kind, kw, shape):
     w = torch.as_tensor(((e - e.mean()) / N).astype(np.complex64), device="cuda")
     grads = {}
     for mode in ("generic", "smem"):
-        gm.tuning = dict(flags=q.FLAG_BACKWARD_GENERIC) if mode == "generic" else {}
+        gm.tuning = dict(flags=q.FLAG_BACKWARD_GENERIC) if mode == "generic" else dict(flags=q.FLAG_BACKWARD_SMEM)
         grads[mode] = q.logpsi_gradient(gm, torch.as_tensor(states, device="cuda"), w, system_shape=shape).cpu().numpy()
     scale = np.abs(grads["generic"]).max()
     assert np.abs(grads["smem"] - grads["generic"]).max() <= 2e-6 * scale
     want, _ = oracle.vmc_gradient(om.astype(np.float64), padded(om, states, shape), e)
     assert np.abs(grads["smem"] - want).max() <= 1e-4 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("layers,shape,N", [([16, 16, 16, 16, 16, 8], (20, 20), 37), ([8, 8, 8], (10, 10), 333),
+                                            ([16, 16, 8], (9, 11), 5), ([16, 16, 16], (7, 23), 41), ([8, 8], (3, 3), 7),
+                                            ([16, 16, 16, 16, 16, 8], (40, 40), 3), ([16, 8], (37, 5), 9)])
+def test_band_backward_matches_per_sample_kernels_and_oracle(layers, shape, N):
+    """The per-layer band kernels (k_bwd_head / k_bwd_layer / k_bwd_layer0: register-resident weight-gradient tiles,
+    TMA-staged row bands; default for DCRBM k = 3) against the per-sample kernels (QMC_FLAG_BACKWARD_SMEM, and the
+    L2-resident k_backward where the planes do not fit) and against the oracle's float64 gradient of loss_op.
+    40 x 40 runs in three bands; 37 x 5 and 7 x 23 exercise ragged bands and row lengths that are no multiple of 3."""
+    import oracle
+    from gpu_util import make_pair, rand_states, padded
+    q = _q()
+    gm, om = make_pair("dcrbm", shape[0], 1e-1, 33, layers=layers)
+    rng = np.random.default_rng(9)
+    states = rand_states(rng, N, shape)
+    e = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    w = torch.as_tensor(((e - e.mean()) / N).astype(np.complex64), device="cuda")
+    st = torch.as_tensor(states, device="cuda")
+    lib = q._lib.load()
+    n0 = lib.qmc_launch_count()
+    got = q.logpsi_gradient(gm, st, w, system_shape=shape).cpu().numpy()
+    launches = lib.qmc_launch_count() - n0
+    assert launches == 1 + 1 + 1 + len(layers) + 1, launches      # repack, forward, head, one per layer, reduce
+    again = q.logpsi_gradient(gm, st, w, system_shape=shape).cpu().numpy()
+    assert np.array_equal(got, again)                               # fixed summation order: reproducible bit for bit
+    gm.tuning = dict(flags=q.FLAG_BACKWARD_SMEM)
+    ref = q.logpsi_gradient(gm, st, w, system_shape=shape).cpu().numpy()
+    assert np.abs(got - ref).max() <= 5e-5 * np.abs(ref).max()        # another summation order over N * L^2 fp32 terms
+    if shape[0] * shape[1] <= 500:
+        want, _ = oracle.vmc_gradient(om.astype(np.float64), padded(om, states, shape), e)
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
 
 
 @pytest.mark.parametrize("sync,warps,S", [("3", "1", 333), ("0", "1", 333), ("3", "11", 1700), ("3", "12", 3700)])

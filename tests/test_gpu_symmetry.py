@@ -132,7 +132,9 @@ def test_sym_one_launch_paths_equal_image_composition(kind, L, kw):
         e, n = launches(lambda: fn(sm, st, system_shape=shape, **kwargs))
         assert n <= 3, (ham, n)
         want = sm.local_energy_composed(fn, st, shape, **kwargs)
-        assert (e - want).abs().max().item() < 1e-5 * max(1.0, want.abs().max().item()), ham
+        # element by element: where the images nearly cancel in sum_g psi_g, |E_loc| reaches 1e3-1e4 and both sides carry
+        # the fp32 rounding of the image amplitudes amplified by that cancellation
+        assert ((e - want).abs() / want.abs().clamp(min=1.0)).max().item() < 2e-4, ham
     g, n = launches(lambda: q.logpsi_gradient(sm, st, w, shape))
     assert n <= 4, n
     want = sm.gradient_composed(lambda im, s_, w_, sh: q.logpsi_gradient(im, s_, w_, sh), st, w, shape)
