@@ -245,6 +245,9 @@ int qmc_diag_peaks2(int device, double* fp32_tflops, double* ffma2_tflops, doubl
  * layer 0, layer barriers, conv accumulation loops, tanh epilogues, head, accept + commit; out[8]: proposals;
  * out[9 + w]: task duration (cycles) of warp w of a CTA, summed over CTAs and launches. */
 int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/);
+/* Every float through the evaluator's tanh epilogue (small-argument fast path + tanhf) against tanhf: number of
+ * bit-level mismatches (must be 0). */
+int qmc_diag_tanh_check(int device, unsigned long long* mismatches /*host*/);
 
 /* number of CUDA kernels this library has launched in this process (graph replays count
  * their kernel nodes) */

@@ -94,6 +94,7 @@ SIGNATURES = {
     "qmc_diag_peaks": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_diag_peaks2": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qmc_diag_ip_profile": (_i, [C.POINTER(C.c_ulonglong)]),
+    "qmc_diag_tanh_check": (_i, [_i, C.POINTER(C.c_ulonglong)]),
     "qmc_launch_count": (C.c_ulonglong, []),
     "qmc_version": (C.c_char_p, []),
 }

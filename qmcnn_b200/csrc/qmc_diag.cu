@@ -3,6 +3,7 @@
 // unrolled register-only loops.  Diagnostics only; not on the hot path.
 #include <cuda_runtime.h>
 #include "qmcnn_b200.h"
+#include "qmc_ip.cuh"
 
 namespace {
 
@@ -114,4 +115,37 @@ extern "C" int qmc_diag_peaks(int device, double* fp32_tflops, double* mufu_gops
 
 extern "C" int qmc_diag_peaks2(int device, double* fp32_tflops, double* ffma2_tflops, double* mufu_gops) {
     return diag_peaks_impl(device, fp32_tflops, mufu_gops, ffma2_tflops);
+}
+
+
+// every float: ip_tanh4 (the small-argument fast path of the in-place evaluator's epilogue) against tanhf, bit for bit
+__global__ void k_tanh_check(unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)i);
+        const float4 r = qmc::ip_tanh4(make_float4(x, x * 0.5f, -x, 0.f));
+        const float w0 = tanhf(x), w1 = tanhf(x * 0.5f), w2 = tanhf(-x);
+        const bool ok0 = __float_as_uint(r.x) == __float_as_uint(w0) || (r.x != r.x && w0 != w0);
+        const bool ok1 = __float_as_uint(r.y) == __float_as_uint(w1) || (r.y != r.y && w1 != w1);
+        const bool ok2 = __float_as_uint(r.z) == __float_as_uint(w2) || (r.z != r.z && w2 != w2);
+        if (!(ok0 && ok1 && ok2)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int qmc_diag_tanh_check(int device, unsigned long long* mismatches /*host*/) {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) return QMC_ERR_BAD_ARGUMENT;
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 8);
+    if (e == cudaSuccess) e = cudaMemset(d, 0, 8);
+    if (e == cudaSuccess) {
+        k_tanh_check<<<148 * 8, 256>>>(d);
+        e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    cudaSetDevice(prev);
+    return e == cudaSuccess ? QMC_OK : QMC_ERR_CUDA;
 }

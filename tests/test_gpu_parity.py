@@ -706,3 +706,13 @@ def test_plane_forward_is_bit_identical_to_blocked_forward(layers, shape):
     assert np.array_equal(outs[0][0].view(np.float32), outs[1][0].view(np.float32))
     assert np.array_equal(outs[0][2], outs[1][2])
     assert np.abs(outs[0][1] - outs[1][1]).max() < 2e-6 * max(1.0, np.abs(outs[1][1]).max())
+
+
+def test_tanh_fast_path_is_bit_identical_to_tanhf_for_every_float():
+    """The evaluator's tanh epilogue takes tanhf's own small-argument polynomial when a lane's four values are below
+    tanhf's branch point and calls tanhf otherwise; qmc_diag_tanh_check runs all 2^32 floats (and x/2, -x) through it."""
+    import ctypes
+    q = _q()
+    bad = ctypes.c_ulonglong(123)
+    assert q._lib.load().qmc_diag_tanh_check(0, ctypes.byref(bad)) == 0
+    assert bad.value == 0
