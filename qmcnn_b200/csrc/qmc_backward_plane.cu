@@ -67,6 +67,7 @@ __device__ __forceinline__ void band_load_issue(float* dst, const float* __restr
     for (int i = threadIdx.x; i < ncg * nrows; i += blockDim.x) {
         const int cg = i / nrows, r = i - cg * nrows;
         const int gy = wrap1(y0 - 1 + r, Ly);
+        QMC_ASSERT(gy >= 0 && gy < Ly && r * PW + 1 + Lx <= PA, "band row inside lattice and buffer");
         const unsigned d = smem_addr_u32(dst + ((size_t)cg * PA + r * PW + 1) * 4);
         const float* src = plane + ((size_t)cg * n + (size_t)gy * Lx) * 4;
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -137,6 +138,7 @@ struct DwTile {
         const float4* A4 = reinterpret_cast<const float4*>(A) + (size_t)cig * PA;
         const float* Gc = G + ((size_t)(cp >> 1) * PA) * 4 + (cp & 1) * 2;
         for (int y = worker; y < BH; y += nworkers) {
+            QMC_ASSERT((y + 2) * PW + ((Lx + 2) / 3) * 3 + 4 < PA + PW, "sliding window inside the band (+ slack row)");
             const float4* ar = A4 + y * PW;                    // padded rows y, y + 1, y + 2 are taps dy = 0, 1, 2
             const float* gr = Gc + (size_t)((y + 1) * PW + 1) * 4;
             float4 c0[3], c1[3], c2[3];
@@ -209,7 +211,7 @@ struct BwdSmem {
     float* A;           // padded band of the layer's input
     float* G;           // padded band of the cotangent
     float* red;         // reduction scratch
-    unsigned short* tab;
+    site_t* tab;
     unsigned long long* bar;
 };
 
@@ -220,7 +222,7 @@ __device__ __forceinline__ BwdSmem bwd_carve(float* base, const BwdPlan& bp, int
     s.A = s.wt + wt_floats;
     s.G = s.A + bp.plane_floats;
     s.red = s.G + bp.plane_floats;
-    s.tab = reinterpret_cast<unsigned short*>(s.red + red_floats);
+    s.tab = reinterpret_cast<site_t*>(s.red + red_floats);
     return s;
 }
 
@@ -239,10 +241,10 @@ __device__ __forceinline__ void bwd_zero(float* p, int nfloats) {
 
 template <int K, int CI, int CO, typename OutF>
 __device__ __forceinline__ void bwd_conv(int P, int wbase, int bbase, const float* wsm, const float* tin, int PW, int PA,
-                                         int Lx, int lane, OutF out, const unsigned short* tab) {
+                                         int Lx, int lane, OutF out, const site_t* tab, int cap4) {
     NoMid mid;
-    if (P == 4) conv_region_split<K, CI, CO, 2, 4>(wbase, bbase, wsm, tin, PW, PA, Lx, lane, out, mid, tab);
-    else conv_region_split<K, CI, CO, 2, 6>(wbase, bbase, wsm, tin, PW, PA, Lx, lane, out, mid, tab);
+    if (P == 4) conv_region_split<K, CI, CO, 2, 4>(wbase, bbase, wsm, tin, PW, PA, Lx, lane, out, mid, tab, cap4);
+    else conv_region_split<K, CI, CO, 2, 6>(wbase, bbase, wsm, tin, PW, PA, Lx, lane, out, mid, tab, cap4);
 }
 
 // ---- head: theta of the last layer over the band, G_D = (Re, Im)(w conj tanh theta) --------------------------------
@@ -250,7 +252,7 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kBwdPlaneWarps * 32, 2)
 k_bwd_head(DevModel m, const float* __restrict__ params, const float2* __restrict__ weights, int N,
            const float* __restrict__ cache_all, float* __restrict__ g_out, BwdPlan bp,
-           const unsigned short* __restrict__ tab_g, ImageStrides is, size_t gimg) {
+           const site_t* __restrict__ tab_g, ImageStrides is, size_t gimg) {
     extern __shared__ float4 smem4[];
     params += (size_t)blockIdx.y * is.params;
     cache_all += (size_t)blockIdx.y * is.cache;
@@ -267,7 +269,7 @@ k_bwd_head(DevModel m, const float* __restrict__ params, const float2* __restric
     bwd_zero(sm.G, bp.plane_floats);
     bwd_bar_init(sm.bar);
     const unsigned bar_a = smem_addr_u32(sm.bar);
-    const unsigned short* tab = sm.tab + warp * bp.P * 16;
+    const site_t* tab = sm.tab + warp * bp.P * 16;
     const int n = m.n, Ly = m.Ly, Lx = m.Lx, PW = bp.PW, PA = bp.PA, half = COUT / 2;
     const float* inoff = cache_all + m.layer[m.D - 2].act_off;
     unsigned phase = 0;
@@ -282,7 +284,8 @@ k_bwd_head(DevModel m, const float* __restrict__ params, const float2* __restric
         band_fill_halo_cols(sm.A, CIN / 4, bp.BH, Lx, PW, PA);
         __syncthreads();
         bwd_conv<3, CIN, COUT>(bp.P, 0, 9 * CIN * COUT, sm.wt, sm.A, PW, PA, Lx, lane,
-                               [&](int pos, int, int, int cog, float4 a) { if (pos < bsites) th4[cog * bsites + pos] = a; }, tab);
+                               [&](int pos, int, int, int cog, float4 a) { if (pos < bsites) th4[cog * bsites + pos] = a; }, tab,
+                               bp.plane_floats >> 2);
         __syncthreads();
         const float2 w = weights[s];
         float* gs = g_out + (size_t)s * bp.gfloats;
@@ -303,7 +306,7 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kBwdPlaneWarps * 32, 2)
 k_bwd_layer(DevModel m, int l, const float* __restrict__ params, int N, const float* __restrict__ cache_all,
             const float* __restrict__ g_in, float* __restrict__ g_out, float* __restrict__ partial, BwdPlan bp,
-            const unsigned short* __restrict__ tab_g, ImageStrides is, size_t gimg) {
+            const site_t* __restrict__ tab_g, ImageStrides is, size_t gimg) {
     extern __shared__ float4 smem4[];
     params += (size_t)blockIdx.y * is.params;
     cache_all += (size_t)blockIdx.y * is.cache;
@@ -325,7 +328,7 @@ k_bwd_layer(DevModel m, int l, const float* __restrict__ params, int N, const fl
     bwd_zero(sm.G, bp.plane_floats);
     bwd_bar_init(sm.bar);
     const unsigned bar_a = smem_addr_u32(sm.bar);
-    const unsigned short* tab = sm.tab + warp * bp.P * 16;
+    const site_t* tab = sm.tab + warp * bp.P * 16;
     const int n = m.n, Ly = m.Ly, Lx = m.Lx, PW = bp.PW, PA = bp.PA;
     const float* inoff = cache_all + m.layer[l - 1].act_off;
     unsigned phase = 0;
@@ -350,6 +353,7 @@ k_bwd_layer(DevModel m, int l, const float* __restrict__ params, int N, const fl
                 const bool isa = i < na;
                 const int k = isa ? i : i - na, cg = k / nrows, r = k - cg * nrows;
                 const int gy = wrap1(y0 - 1 + r, Ly);
+                QMC_ASSERT(gy >= 0 && gy < Ly && ((size_t)cg * PA + r * PW + 1 + Lx) * 4 <= (size_t)bp.plane_floats, "band row inside lattice and buffer");
                 const unsigned d = smem_addr_u32((isa ? sm.A : sm.G) + ((size_t)cg * PA + r * PW + 1) * 4);
                 const float* src = (isa ? pa : pg) + ((size_t)cg * n + (size_t)gy * Lx) * 4;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -371,7 +375,7 @@ k_bwd_layer(DevModel m, int l, const float* __restrict__ params, int N, const fl
                                    const float4 act = A4[cog * PA + (y + 1) * PW + x + 1];
                                    go4[cog * n + y0 * Lx + pos] = make_float4((1.f - act.x * act.x) * a.x, (1.f - act.y * act.y) * a.y,
                                                                               (1.f - act.z * act.z) * a.z, (1.f - act.w * act.w) * a.w);
-                               }, tab);
+                               }, tab, bp.plane_floats >> 2);
         __syncthreads();
     }
     dw.flush(sm.red, partial, L, lane, warp, nwarps);
@@ -451,7 +455,7 @@ static BwdPlan bwd_plan(const qmc_handle* h) {
         if (BH * m.Lx > kBwdPlaneWarps * 6 * 16) continue;
         const int PA = (BH + 2) * bp.PW;
         const int plane = round4((PA + bp.PW) * cmax);
-        const size_t smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)plane + round4(9 * 16 * 16 + 16)) * 4 + 2 * kBwdPlaneWarps * 6 * 16;
+        const size_t smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)plane + round4(9 * 16 * 16 + 16)) * 4 + sizeof(site_t) * kBwdPlaneWarps * 6 * 16;
         if (smem > budget) continue;
         bp.BH = BH; bp.nbands = nb; bp.PA = PA; bp.plane_floats = plane;
         break;
@@ -472,7 +476,7 @@ static BwdPlan bwd_plan(const qmc_handle* h) {
     // the conv needs `warps`; the weight gradient likes all eight: tables cover 8 warps, surplus ones hold no sites
     bp.tab_entries = (kBwdPlaneWarps * bp.P * 16 + 7) & ~7;
     bp.gfloats = cmax * m.n;
-    bp.smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)bp.plane_floats + round4(9 * 16 * 16 + 16)) * 4 + (size_t)bp.tab_entries * 2;
+    bp.smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)bp.plane_floats + round4(9 * 16 * 16 + 16)) * 4 + (size_t)bp.tab_entries * sizeof(site_t);
     (void)warps;
     bp.ok = 1;
     return bp;
@@ -481,10 +485,10 @@ static BwdPlan bwd_plan(const qmc_handle* h) {
 bool backward_plane_supported(const qmc_handle* h) { return bwd_plan(h).ok != 0; }
 
 // plane_site_table of qmc_plane.cu, for the band tile
-static void band_site_table(int s0, int s1, int Lx, int PW, int P, unsigned short* tab) {
+static void band_site_table(int s0, int s1, int Lx, int PW, int P, site_t* tab) {
     const int cnt = s1 > s0 ? s1 - s0 : 0, G = (cnt + P - 1) / P;
     std::vector<char> taken(cnt > 0 ? cnt : 1, 0);
-    for (int i = 0; i < P * 16; ++i) tab[i] = 0xFFFF;
+    for (int i = 0; i < P * 16; ++i) tab[i] = kNoSite;
     int left = cnt;
     for (int j = 0; j < P; ++j)
         for (int h0 = 0; h0 < 16; h0 += 8) {
@@ -502,7 +506,7 @@ static void band_site_table(int s0, int s1, int Lx, int PW, int P, unsigned shor
                 used |= 1u << ((y * PW + x) & 7);
                 taken[pick] = 1;
                 --left;
-                tab[j * 16 + slot] = (unsigned short)((y << 8) | x);
+                tab[j * 16 + slot] = make_site(y, x, PW);
             }
         }
 }
@@ -511,15 +515,15 @@ cudaError_t bwd_plane_upload_tables(qmc_handle* h) {
     h->d_bwd_tab = nullptr;
     const BwdPlan bp = bwd_plan(h);
     if (!bp.ok) return cudaSuccess;
-    std::vector<unsigned short> tab(bp.tab_entries, 0xFFFF);
+    std::vector<site_t> tab(bp.tab_entries, kNoSite);
     const int bs = bp.BH * h->m.Lx;
     for (int w = 0; w < kBwdPlaneWarps; ++w) {
         const int s0 = w * bp.chunk < bs ? w * bp.chunk : bs, s1 = s0 + bp.chunk < bs ? s0 + bp.chunk : bs;
         band_site_table(s0, s1, h->m.Lx, bp.PW, bp.P, tab.data() + (size_t)w * bp.P * 16);
     }
-    cudaError_t e = cudaMalloc(&h->d_bwd_tab, tab.size() * sizeof(unsigned short));
+    cudaError_t e = cudaMalloc(&h->d_bwd_tab, tab.size() * sizeof(site_t));
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(h->d_bwd_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
+    return cudaMemcpy(h->d_bwd_tab, tab.data(), tab.size() * sizeof(site_t), cudaMemcpyHostToDevice);
 }
 
 static int bwd_plane_ctas(const qmc_handle* h, int nimg, long long ntasks) {

@@ -27,13 +27,13 @@ struct qmc_handle {
     int ip_stagger = 40;         // reserved[2] >> 8: start offset between the phase groups of k_sweep_ip (x 1024 cycles)
     int ip_chunks = 64;          // reserved[3]: at most this many chunks per chain of the time-sliced sweep
     bool ip_cf = true;           // !QMC_FLAG_IP_ROWMAJOR_SITES: conflict-free site tables for the in-place evaluator
-    unsigned short* d_ip_tab = nullptr;   // device image of the tables (ip_upload_tables), or nullptr
+    qmc::site_t* d_ip_tab = nullptr;   // device image of the tables (ip_upload_tables), or nullptr
     int energy_path = 0;         // 0 auto, 1 classic persistent (QMC_FLAG_ENERGY_CLASSIC), 2 in-place (QMC_FLAG_ENERGY_INPLACE)
     bool backward_generic = false;   // QMC_FLAG_BACKWARD_GENERIC
     bool backward_smem_only = false; // QMC_FLAG_BACKWARD_SMEM: k_backward_smem / k_backward instead of the per-layer band kernels
-    unsigned short* d_bwd_tab = nullptr;     // site tables of the band kernels (bwd_plane_upload_tables), or nullptr
+    qmc::site_t* d_bwd_tab = nullptr;     // site tables of the band kernels (bwd_plane_upload_tables), or nullptr
     bool forward_blocked = false;    // QMC_FLAG_FORWARD_BLOCKED: k_forward (8 x 8 blocks) instead of k_forward_plane
-    unsigned short* d_plane_tab = nullptr;   // site tables of k_forward_plane (plane_upload_tables), or nullptr
+    qmc::site_t* d_plane_tab = nullptr;   // site tables of k_forward_plane (plane_upload_tables), or nullptr
 };
 
 namespace qmc {

@@ -132,6 +132,9 @@ __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip
             dx = cc < p ? cc - b : a + 1 + (cc - p);
         }
         const int site = wrap1(y0 + dy, Ly) * Lx + wrap1(x0 + dx, Lx);
+        QMC_ASSERT(site >= 0 && site < n, "frame gather: lattice site");
+        QMC_ASSERT(ip.c + dy >= 0 && ip.c + dy < ip.T && ip.c + dx >= 0 && ip.c + dx < ip.T, "frame gather: arena position");
+        QMC_ASSERT((ncg * ip.tarea) * 4 <= ip.arena_floats, "frame gather: arena planes");
         float4* dst = arena4 + (ip.c + dy) * ip.T + (ip.c + dx);
         const float* src = plane + (size_t)site * 4;
         for (int cg = 0; cg < ncg; ++cg) cp_async16(dst + cg * ip.tarea, src + (size_t)cg * n * 4);
@@ -152,7 +155,7 @@ __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip
 // Per (tap, 4 input channels): 8 x 2 + 2P x 2 wavefronts instead of 16 x 2 + P x 4 (P = sites per lane before): 20 / 24
 // / 28 / 32 instead of 36 / 40 / 44 / 48 for the 5x5 ... 11x11 windows.  The fma chain of an output value is unchanged
 // (bias, taps ascending, input channels ascending), so results stay bit-identical.
-//   tab: entry [j * NS + slot] = (y << 8) | x of the slot's j-th site or 0xFFFF, NS = 32 / CS slots.
+//   tab: entry [j * NS + slot] = make_site(y, x, tile pitch) of the slot's j-th site or kNoSite, NS = 32 / CS slots.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef QMC_IP_SPLIT
 #define QMC_IP_SPLIT 2        // 0: one-part tiles (conv_region_tiled); 2: two channel parts; 4: four parts for small windows
@@ -162,7 +165,8 @@ __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip
 template <int K, int CIN, int COUT, int CS, int P, typename OutF, typename MidF>
 __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const float* wsm, const float* tin, int tw,
                                                   int tarea, int side, int lane, OutF out, MidF mid,
-                                                  const unsigned short* tab) {
+                                                  const site_t* tab, int cap4 = 0x7fffffff) {
+    // cap4 (debug builds): float4 words of the input tile buffer - every input read is checked against it
     static_assert(CS == 2 || CS == 4, "channel parts");
     constexpr int CL = COUT / CS;             // output channels of this lane
     constexpr int NS = kWarp / CS;            // site slots
@@ -171,17 +175,20 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
     // aligned lane quads hold two slots x two parts (lds_patterns.cu)
     const int part = CS == 2 ? (lane & 1) : ((lane >> 1) & 3);
     const int slot = CS == 2 ? (lane >> 1) : ((lane & 1) | ((lane >> 3) << 1));
-    const float4* tin4 = reinterpret_cast<const float4*>(tin);
-    int toff[P];
+    // the lane's P input positions as pointers: one address add per (site, tap, channel group) in the loop below
+    const float4* pin[P];
     unsigned valid = 0;                       // bit j: site j of this slot is a real output
     {
-        const unsigned first = tab[slot];
+        const float4* tin4 = reinterpret_cast<const float4*>(tin);
+        const site_t first = tab[slot];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
-            unsigned pk = tab[j * NS + slot];
-            if (pk != 0xFFFFu) valid |= 1u << j;
-            else pk = first != 0xFFFFu ? first : 0u;       // duplicate work, result discarded below
-            toff[j] = (int)(pk >> 8) * tw + (int)(pk & 255u);
+            site_t pk = tab[j * NS + slot];
+            if (pk != kNoSite) valid |= 1u << j;
+            else pk = first != kNoSite ? first : 0u;       // duplicate work, result discarded below
+            QMC_ASSERT((int)(pk >> 16) == (int)((pk >> 8) & 255u) * tw + (int)(pk & 255u), "site table: offset = y * pitch + x");
+            QMC_ASSERT((int)(pk >> 16) + (K - 1) * tw + (K - 1) + (NCG - 1) * tarea < cap4, "conv input window inside the tile buffer");
+            pin[j] = tin4 + (pk >> 16);
         }
     }
     const int wlane = wbase + part * CL, blane = bbase + part * CL;
@@ -203,13 +210,13 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
         { const int v_ = *(volatile int*)&s_ip_conv[sched_]; ++conc_[v_ < 1 ? 0 : v_ > 4 ? 3 : v_ - 1]; }
 #endif
         const int dy = d / K, dx = d - dy * K;
-        const float4* tp = tin4 + dy * tw + dx;
+        const int toff = dy * tw + dx;
         const int wrow = wlane + d * CIN * COUT;
 #pragma unroll(kCgUnroll)
         for (int cg = 0; cg < NCG; ++cg) {
             float4 in[P];
 #pragma unroll
-            for (int j = 0; j < P; ++j) in[j] = tp[cg * tarea + toff[j]];
+            for (int j = 0; j < P; ++j) in[j] = pin[j][cg * tarea + toff];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 float2 w[CL / 2];
@@ -239,8 +246,8 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
 #pragma unroll
     for (int j = 0; j < P; ++j) {
         if (!((valid >> j) & 1u)) continue;
-        const unsigned pk = tab[j * NS + slot];          // re-read: cheaper than P live registers across the loop
-        const int y = (int)(pk >> 8), x = (int)(pk & 255u);
+        const site_t pk = tab[j * NS + slot];            // re-read: cheaper than P live registers across the loop
+        const int y = (int)((pk >> 8) & 255u), x = (int)(pk & 255u);
         const int pos = y * side + x;
 #pragma unroll
         for (int q4 = 0; q4 < CL / 4; ++q4)
@@ -284,18 +291,18 @@ __host__ __device__ inline IpTile ip_tile(int acc, int cout, int npos) {
 template <int K, int CIN, int COUT, int ACC, typename OutF, typename MidF>
 __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const float* wsm, const float* tin,
                                                     int tw, int tarea, int side, int lane, OutF out, MidF mid,
-                                                    const unsigned short* tab) {
+                                                    const site_t* tab, int cap4 = 0x7fffffff) {
     const int npos = side * side;
 #if QMC_IP_SPLIT
     constexpr int CL = COUT / 2;
     if constexpr (QMC_IP_SPLIT >= 4 && COUT == 16) {
-#define QMC_SPLIT4(PP) conv_region_split<K, CIN, COUT, 4, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab)
+#define QMC_SPLIT4(PP) conv_region_split<K, CIN, COUT, 4, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
         if (npos <= 4 * 8) return QMC_SPLIT4(4);
         if (npos <= 7 * 8) return QMC_SPLIT4(7);
         if (npos <= 11 * 8) return QMC_SPLIT4(11);
 #undef QMC_SPLIT4
     }
-#define QMC_SPLIT(PP) conv_region_split<K, CIN, COUT, 2, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab)
+#define QMC_SPLIT(PP) conv_region_split<K, CIN, COUT, 2, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
     if (npos <= 2 * 16) return QMC_SPLIT(2);
     if (npos <= 4 * 16) return QMC_SPLIT(4);
     if (npos <= 6 * 16) return QMC_SPLIT(6);
@@ -358,6 +365,7 @@ __device__ __forceinline__ void ip_scatter_layer(const DevModel& m, const LayerI
     for (int pos = lane; pos < rarea; pos += kWarp) {
         const int y = dside.div(pos), x = pos - y * side;
         const int site = wrap1(ry + y, m.Ly) * m.Lx + wrap1(rx + x, m.Lx);
+        QMC_ASSERT(site >= 0 && site < n && L.act_off >= 0, "commit scatter: cache site");
         for (int cg = 0; cg < ncg; ++cg) plane4[cg * n + site] = src[ip_stage_index(pos, cg, rarea, ncg, cs)];
     }
 }
@@ -370,7 +378,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                                                   const unsigned* mg, float* arena, float* spt, const int8_t* spins_s,
                                                   const float* __restrict__ cache, float* staging,
                                                   int site_f, int lane, int gid, int gthreads, float& dre,
-                                                  float* dim_out, const int* tabo, const unsigned short* tab_s,
+                                                  float* dim_out, const int* tabo, const site_t* tab_s,
                                                   IpProf& prof) {
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n, D = m.D;
     const int T = ip.T, TA = ip.tarea, c = ip.c;
@@ -383,6 +391,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         for (int idx = lane; idx < stw * stw; idx += kWarp) {
             const int ty = dtw.div(idx), tx = idx - ty * stw;
             const int site = wrap1(y0 - 2 * p + ty, Ly) * Lx + wrap1(x0 - 2 * p + tx, Lx);
+            QMC_ASSERT(site >= 0 && site < n && idx < ip.spt_floats, "spin tile");
             int s = spins_s[site];
             if (site == site_f) s = -s;
             spt[idx] = (float)s;
@@ -404,6 +413,10 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         conv_region_generic(L, m.k, sp, spt, stw, stw * stw, side, side, lane,
                             [&](int pos, int y, int x, int cog, float4 a) {
                                 a = ip_tanh4(a);
+                                QMC_ASSERT((cog * TA + (y + o0) * T + (x + o0)) * 4 + 3 < ip.arena_floats && y + o0 < T && x + o0 < T,
+                                           "layer 0 output inside the arena");
+                                QMC_ASSERT(!SWEEP || ip_stage_index(pos, cog, rarea, L.coutp >> 2, 1) * 4 + 3 < ip.staging_floats,
+                                           "layer 0 output inside the staging");
                                 arena4[cog * TA + (y + o0) * T + (x + o0)] = a;
                                 if (SWEEP) stg4[ip_stage_index(pos, cog, rarea, L.coutp >> 2, 1)] = a;
                             });
@@ -422,7 +435,9 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         side += 2 * p;
         const int rarea = side * side;
         const float* tin = arena + (size_t)((c - hn - p) * T + (c - hn - p)) * 4;
-        const unsigned short* tab = (tabo && tabo[l] >= 0) ? tab_s + tabo[l] : nullptr;   // conflict-free site deal
+        const int cap4 = (ip.arena_floats >> 2) - ((c - hn - p) * T + (c - hn - p));      // float4 words from tin to the arena's end
+        QMC_ASSERT(c - hn - p >= 0, "layer input box inside the arena");
+        const site_t* tab = (tabo && tabo[l] >= 0) ? tab_s + tabo[l] : nullptr;   // conflict-free site deal
         auto sync = [&] { __syncwarp(); prof.mark(4); };
         if (!last) {
             const float* plane = cache + L.act_off;
@@ -432,6 +447,10 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
             const int tcs = ip_tile(ACC, L.cout, rarea).cs;
             auto out = [&](int pos, int y, int x, int cog, float4 a) {
                 a = ip_tanh4(a);
+                QMC_ASSERT((cog * TA + (y + o0) * T + (x + o0)) * 4 + 3 < ip.arena_floats && y + o0 < T && x + o0 < T && pos < rarea,
+                           "hidden-layer output inside the arena");
+                QMC_ASSERT(!SWEEP || stg + ip_stage_index(pos, cog, rarea, ncg, tcs) * 4 + 3 < ip.staging_floats,
+                           "hidden-layer output inside the staging");
                 arena4[cog * TA + (y + o0) * T + (x + o0)] = a;
                 if (SWEEP) stg4[ip_stage_index(pos, cog, rarea, ncg, tcs)] = a;
             };
@@ -442,19 +461,22 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                 ip_gather_frame(arena4, ip, plane, ncg, n, hn, p, mg[l], y0, x0, Ly, Lx, lane);
             };
             if (L.cin == 16 && L.cout == 16)
-                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab);
+                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab, cap4);
             else
-                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab);
+                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab, cap4);
             stg += L.coutp * rarea;
             cp_async_wait_all();
         } else {
-            auto out = [&](int pos, int, int, int cog, float4 a) { arena4[cog * rarea + pos] = a; };
+            auto out = [&](int pos, int, int, int cog, float4 a) {
+                QMC_ASSERT((cog * rarea + pos) * 4 + 3 < ip.newf_off && pos < rarea, "last-layer theta below the new factors");
+                arena4[cog * rarea + pos] = a;
+            };
             if (L.cin == 16 && L.cout == 16)
-                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
+                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
             else if (L.cin == 16 && L.cout == 8)
-                conv_region_pick_ip<3, 16, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
+                conv_region_pick_ip<3, 16, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
             else
-                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab);
+                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
         }
         __syncwarp();
         prof.mark(5);
@@ -464,6 +486,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
     // commit, part 1 (speculative): the staged windows of the first layers start their way from L2 into the
     // free part of the arena now, so that an accepted move finds them in shared memory after the head
     if (SWEEP) {
+        QMC_ASSERT(ip.spec_off + ip.spec_floats <= ip.newf_off && ip.spec_floats <= ip.staging_floats, "speculative commit copy");
         for (int i = lane * 4; i < ip.spec_floats; i += kWarp * 4) cp_async16(arena + ip.spec_off + i, staging + i);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -493,6 +516,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         if (pos < npos) {
             if (SWEEP) {
                 const float re = ip_site_re(arena, npos, pos, half);
+                QMC_ASSERT(ip.newf_off + pos < ip.arena_floats, "new factors inside the arena");
                 newf[pos] = re;
                 sre += re - ore[j];
             } else {

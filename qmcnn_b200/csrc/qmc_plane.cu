@@ -33,7 +33,10 @@ __device__ __forceinline__ void plane_halo_store(float4* plane, int PW, int Ly, 
         if (ys[i] < 0) continue;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            if (xs[j] >= 0) plane[idx_of(ys[i] * PW + xs[j])] = a;
+            if (xs[j] >= 0) {
+                QMC_ASSERT(ys[i] < Ly + 2 * p && xs[j] < PW, "halo store inside the padded plane");
+                plane[idx_of(ys[i] * PW + xs[j])] = a;
+            }
     }
 }
 
@@ -50,7 +53,7 @@ struct PlanePlan {
 __global__ void __launch_bounds__(kPlaneMaxWarps * 32, 2)
 k_forward_plane(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
                 float* __restrict__ cache_all, float2* __restrict__ factors, float2* __restrict__ logpsi,
-                PlanePlan pp, const unsigned short* __restrict__ tab_g, ImageStrides is) {
+                PlanePlan pp, const site_t* __restrict__ tab_g, ImageStrides is) {
     extern __shared__ float4 smem4[];
     float* sp = reinterpret_cast<float*>(smem4);
     params += (size_t)blockIdx.y * is.params;                  // symmetry images: own parameter block, cache, outputs
@@ -63,11 +66,11 @@ k_forward_plane(DevModel m, const float* __restrict__ params, const int8_t* __re
     float* B1 = B0 + pp.plane_floats;
     float* S = B1 + pp.plane_floats;                            // padded spin plane (floats), PA entries
     float* red = S + round4(pp.PA);                             // 2 x 32 partial sums (log psi)
-    unsigned short* tab_s = reinterpret_cast<unsigned short*>(red + 64);
+    site_t* tab_s = reinterpret_cast<site_t*>(red + 64);
     load_params_to_smem(m, params, sp);
     for (int i = tid; i < pp.tab_entries; i += nthr) tab_s[i] = tab_g[i];
     __syncthreads();
-    const unsigned short* tab = tab_s + warp * pp.P * 16;
+    const site_t* tab = tab_s + warp * pp.P * 16;
 
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n, D = m.D, PW = pp.PW, PA = pp.PA;
     const FastDiv dPW(PW), dLx(Lx), dn(n);
@@ -120,8 +123,8 @@ k_forward_plane(DevModel m, const float* __restrict__ params, const int8_t* __re
             NoMid mid;
 #define QMC_PLANE(CI, CO, FN)                                                                                         \
     switch (pp.P) {                                                                                                   \
-        case 4: conv_region_split<3, CI, CO, 2, 4>(L.sw_off, L.sb_off, sp, tin, PW, PA, Lx, lane, FN, mid, tab); break; \
-        default: conv_region_split<3, CI, CO, 2, 6>(L.sw_off, L.sb_off, sp, tin, PW, PA, Lx, lane, FN, mid, tab); break; \
+        case 4: conv_region_split<3, CI, CO, 2, 4>(L.sw_off, L.sb_off, sp, tin, PW, PA, Lx, lane, FN, mid, tab, pp.plane_floats >> 2); break; \
+        default: conv_region_split<3, CI, CO, 2, 6>(L.sw_off, L.sb_off, sp, tin, PW, PA, Lx, lane, FN, mid, tab, pp.plane_floats >> 2); break; \
     }
             if (!last) {
                 if (L.cin == 16) { QMC_PLANE(16, 16, hidden) } else { QMC_PLANE(8, 8, hidden) }
@@ -165,10 +168,10 @@ k_forward_plane(DevModel m, const float* __restrict__ params, const int8_t* __re
 // Deal the chunk [s0, s1) of row-major lattice sites to (round j, slot): the eight slots of a half-warp get sites in
 // eight different 16-byte bank groups of the padded plane ((y * PW + x) mod 8; the tap offset shifts all of them
 // alike), preferring row-major order so that the cache stores of a half-warp stay nearly contiguous.
-static void plane_site_table(int s0, int s1, int Lx, int PW, int P, unsigned short* tab) {
+static void plane_site_table(int s0, int s1, int Lx, int PW, int P, site_t* tab) {
     const int cnt = s1 - s0, G = (cnt + P - 1) / P;
     std::vector<char> taken(cnt > 0 ? cnt : 1, 0);
-    for (int i = 0; i < P * 16; ++i) tab[i] = 0xFFFF;
+    for (int i = 0; i < P * 16; ++i) tab[i] = kNoSite;
     int left = cnt;
     for (int j = 0; j < P; ++j)
         for (int h0 = 0; h0 < 16; h0 += 8) {
@@ -186,7 +189,7 @@ static void plane_site_table(int s0, int s1, int Lx, int PW, int P, unsigned sho
                 used |= 1u << ((y * PW + x) & 7);
                 taken[pick] = 1;
                 --left;
-                tab[j * 16 + slot] = (unsigned short)((y << 8) | x);
+                tab[j * 16 + slot] = make_site(y, x, PW);
             }
         }
 }
@@ -221,7 +224,7 @@ static PlanePlan plane_plan(const qmc_handle* h) {
         }
     if (best < 0 || m.n * 4 > 65535) return pp;                     // more than 8 x 96 sites: k_forward
     pp.tab_entries = (pp.warps * pp.P * 16 + 7) & ~7;
-    pp.smem = ((size_t)m.smem_param_floats + 2 * (size_t)pp.plane_floats + round4(pp.PA) + 64) * 4 + (size_t)pp.tab_entries * 2;
+    pp.smem = ((size_t)m.smem_param_floats + 2 * (size_t)pp.plane_floats + round4(pp.PA) + 64) * 4 + (size_t)pp.tab_entries * sizeof(site_t);
     if (pp.smem > h->max_smem) return pp;
     pp.ok = 1;
     return pp;
@@ -234,14 +237,14 @@ cudaError_t plane_upload_tables(qmc_handle* h) {
     h->d_plane_tab = nullptr;
     const PlanePlan pp = plane_plan(h);
     if (!pp.ok) return cudaSuccess;
-    std::vector<unsigned short> tab(pp.tab_entries, 0xFFFF);
+    std::vector<site_t> tab(pp.tab_entries, kNoSite);
     for (int w = 0; w < pp.warps; ++w) {
         const int s0 = w * pp.chunk, s1 = s0 + pp.chunk < h->m.n ? s0 + pp.chunk : h->m.n;
         plane_site_table(s0 < h->m.n ? s0 : h->m.n, s1, h->m.Lx, pp.PW, pp.P, tab.data() + (size_t)w * pp.P * 16);
     }
-    cudaError_t e = cudaMalloc(&h->d_plane_tab, tab.size() * sizeof(unsigned short));
+    cudaError_t e = cudaMalloc(&h->d_plane_tab, tab.size() * sizeof(site_t));
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(h->d_plane_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
+    return cudaMemcpy(h->d_plane_tab, tab.data(), tab.size() * sizeof(site_t), cudaMemcpyHostToDevice);
 }
 
 cudaError_t launch_forward_plane(const qmc_handle* h, int nimg, const float* padded_blocks, const int8_t* spins, int N,

@@ -29,14 +29,14 @@ __device__ unsigned long long g_ip_prof[kIpProfPhases + 1 + 12];  // cycles per 
 
 // per-CTA words after the parameter block: division magics, site-table offsets, then the site tables (uint16)
 constexpr int kIpCtaWords = 2 * QMC_MAX_LAYERS;
-__host__ __device__ inline size_t ip_cta_bytes(const IpPlan& ip) { return (size_t)kIpCtaWords * 4 + (size_t)ip.tab_entries * 2; }
+__host__ __device__ inline size_t ip_cta_bytes(const IpPlan& ip) { return (size_t)kIpCtaWords * 4 + (size_t)ip.tab_entries * sizeof(site_t); }
 
 // shared-memory images of the division magics, the table offsets and the site tables; returns the first per-warp byte
-__device__ __forceinline__ char* ip_cta_setup(float* after_params, const IpPlan& ip, const unsigned short* __restrict__ tab_g,
-                                              unsigned*& mg, int*& tabo, unsigned short*& tab_s) {
+__device__ __forceinline__ char* ip_cta_setup(float* after_params, const IpPlan& ip, const site_t* __restrict__ tab_g,
+                                              unsigned*& mg, int*& tabo, site_t*& tab_s) {
     mg = reinterpret_cast<unsigned*>(after_params);
     tabo = reinterpret_cast<int*>(mg + QMC_MAX_LAYERS);
-    tab_s = reinterpret_cast<unsigned short*>(mg + kIpCtaWords);
+    tab_s = reinterpret_cast<site_t*>(mg + kIpCtaWords);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int j = 0; j < QMC_MAX_LAYERS; ++j) { mg[j] = ip.mgW[j]; tabo[j] = tab_g ? ip.tab_off[j] : -1; }
@@ -56,7 +56,7 @@ __device__ __forceinline__ char* ip_cta_setup(float* after_params, const IpPlan&
 template <int SYNC>
 __global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
 k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip, IpSlice sl,
-           const unsigned short* __restrict__ tab_g) {
+           const site_t* __restrict__ tab_g) {
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
 #if QMC_IP_PROFILE
@@ -68,7 +68,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // division magics W_j = 2(j+2)p + 1 in shared memory: indexing the kernel-parameter array by layer would
     // make ptxas keep a local-memory copy, and those loads miss L1 (28 KB next to 220 KB of shared memory)
-    unsigned* mg; int* tabo; unsigned short* tab_s;
+    unsigned* mg; int* tabo; site_t* tab_s;
     char* wmem = ip_cta_setup(smem_f + m.smem_param_floats, ip, tab_g, mg, tabo, tab_s) + (size_t)warp * ip.per_warp_bytes;
     float* arena = reinterpret_cast<float*>(wmem);
     float* spt = arena + ip.arena_floats;
@@ -147,6 +147,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
             cp_async_wait_all();                              // (a rejected move's speculative commit copy)
             ip_barrier<SYNC>(gid, gthreads);
             prof.mark(0);
+            QMC_ASSERT(f0 >= 0 && f0 < n, "flip site on the lattice");
             warp_eval_flip_ip<kIpAcc, SYNC>(m, ip, sp, mg, arena, spt, spins_s, cache, staging, f0, lane, gid, gthreads, dre,
                                             nullptr, tabo, tab_s, prof);
             const float amp = expf(dre);                      // |exp(z)| = exp(Re z)
@@ -178,6 +179,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
                         fl += add; sd = s2; ++l1;
                     }
                     __syncwarp();                                  // earlier scatter reads of the arena are done
+                    QMC_ASSERT(fl <= ip.newf_off && stg + fl <= ip.staging_floats, "commit batch inside arena and staging");
                     for (int i = lane * 4; i < fl; i += kWarp * 4) cp_async16(arena + i, staging + stg + i);
                     cp_async_wait_all();
                     __syncwarp();
@@ -303,10 +305,10 @@ IpPlan ip_plan(const qmc_handle* h) {
 // the first unassigned sites whose (y * T + x) mod 8 it does not hold yet.  Row-major preference keeps the staging
 // stores of a group nearly contiguous.  Slots >= G = ceil(npos / P) stay idle.  conflict_free = false
 // (QMC_FLAG_IP_ROWMAJOR_SITES): plain row-major deal, for the before / after measurement.
-static void ip_site_table(int side, int T, int P, int NS, bool conflict_free, unsigned short* tab) {
+static void ip_site_table(int side, int T, int P, int NS, bool conflict_free, site_t* tab) {
     const int npos = side * side, G = (npos + P - 1) / P;
     std::vector<char> taken(npos, 0);
-    for (int i = 0; i < P * NS; ++i) tab[i] = 0xFFFF;
+    for (int i = 0; i < P * NS; ++i) tab[i] = kNoSite;
     int left = npos;
     for (int j = 0; j < P; ++j)
         for (int s0 = 0; s0 < NS; s0 += 8) {
@@ -324,7 +326,7 @@ static void ip_site_table(int side, int T, int P, int NS, bool conflict_free, un
                 used |= 1u << ((y * T + x) & 7);
                 taken[pick] = 1;
                 --left;
-                tab[j * NS + slot] = (unsigned short)((y << 8) | x);
+                tab[j * NS + slot] = make_site(y, x, T);
             }
         }
 }
@@ -334,15 +336,15 @@ cudaError_t ip_upload_tables(qmc_handle* h) {
     h->d_ip_tab = nullptr;
     const IpPlan ip = ip_plan(h);
     if (!ip.ok || ip.tab_entries == 0) return cudaSuccess;
-    std::vector<unsigned short> tab(ip.tab_entries, 0xFFFF);
+    std::vector<site_t> tab(ip.tab_entries, kNoSite);
     for (int l = 1; l < h->m.D; ++l) {
         const int side = 1 + 2 * (l + 1) * h->m.p;
         const IpTile t = ip_tile(kIpAcc, h->m.layer[l].cout, side * side);
         ip_site_table(side, ip.T, t.p, t.ns, h->ip_cf, tab.data() + ip.tab_off[l]);
     }
-    cudaError_t e = cudaMalloc(&h->d_ip_tab, tab.size() * sizeof(unsigned short));
+    cudaError_t e = cudaMalloc(&h->d_ip_tab, tab.size() * sizeof(site_t));
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(h->d_ip_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
+    return cudaMemcpy(h->d_ip_tab, tab.data(), tab.size() * sizeof(site_t), cudaMemcpyHostToDevice);
 }
 
 IpLaunch ip_launch_plan(const qmc_handle* h, int S) {
@@ -414,14 +416,14 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
 __global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
 k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
             const float* __restrict__ cache_all, float2* __restrict__ partial, int nchunks, IpPlan ip,
-            int group_warps, const unsigned short* __restrict__ tab_g) {
+            int group_warps, const site_t* __restrict__ tab_g) {
     extern __shared__ float4 smem4[];
     float* smem_f = reinterpret_cast<float*>(smem4);
     load_params_to_smem(m, params, smem_f);
     const float* sp = smem_f;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    unsigned* mg; int* tabo; unsigned short* tab_s;
+    unsigned* mg; int* tabo; site_t* tab_s;
     char* wmem = ip_cta_setup(smem_f + m.smem_param_floats, ip, tab_g, mg, tabo, tab_s) + (size_t)warp * ip.per_warp_bytes;
     float* arena = reinterpret_cast<float*>(wmem);
     float* spt = arena + ip.arena_floats;

@@ -8,8 +8,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_addoption(parser):
+    parser.addoption("--qmc-lib", default="", help="run against this build of libqmcnn_b200 (e.g. the debug build with "
+                     "device-side bounds checks: make -C qmcnn_b200/csrc debug) instead of the in-tree library")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+    lib = config.getoption("--qmc-lib")
+    if lib:
+        from qmcnn_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(lib)
 
 
 def pytest_collection_modifyitems(config, items):
