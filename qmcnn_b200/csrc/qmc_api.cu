@@ -95,7 +95,13 @@ int qmc_init_spins(int device, int8_t* spins, int S, int n, uint64_t seed, int64
     return e == cudaSuccess ? QMC_OK : cuda_fail(nullptr, e, "init_spins");
 }
 
-const char* qmc_version(void) { return "qmcnn_b200 0.1 (sm_100a)"; }
+const char* qmc_version(void) {
+#if QMC_DEBUG
+    return "qmcnn_b200 0.2 (sm_100a, DEBUG build: device-side bounds checks)";
+#else
+    return "qmcnn_b200 0.2 (sm_100a)";
+#endif
+}
 
 unsigned long long qmc_launch_count(void) { return qmc::g_launches; }
 

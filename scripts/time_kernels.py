@@ -1,5 +1,5 @@
 """Time K1 (forward) and K4 (gradient) alone with CUDA events and print them against the FP32 roofline.
-Usage: python scripts/time_kernels.py [C3|C5|C2] [N] [flags]   (flags: model.tuning flags, e.g. 256 = blocked forward)"""
+Usage: python scripts/time_kernels.py [C3|C5|C2] [N] [flags] [lib]   (flags: model.tuning flags, e.g. 256 = blocked forward)"""
 import sys
 import numpy as np
 import torch
@@ -11,6 +11,9 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 cfg = bench.CONFIGS[name]
 N = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["chains"]
 flags = int(sys.argv[3], 0) if len(sys.argv) > 3 else 0
+if len(sys.argv) > 4:                       # A/B: another build of the library
+    from qmcnn_b200 import _lib
+    _lib.LIB_PATH = sys.argv[4]
 dev = torch.device("cuda", 0)
 Ly, Lx = cfg["shape"]
 model = q.DCRBM(cfg["k"], cfg["layers"], 2, device=dev, seed=0)

@@ -21,6 +21,14 @@ def pytest_configure(config):
         _lib.LIB_PATH = os.path.abspath(lib)
 
 
+def pytest_report_header(config):
+    try:
+        from qmcnn_b200 import _lib
+        return "libqmcnn_b200: %s  [%s]" % (_lib.LIB_PATH, _lib.load().qmc_version().decode())
+    except Exception as e:  # not built yet: the ABI test reports it
+        return "libqmcnn_b200: not loaded (%s)" % e
+
+
 def pytest_collection_modifyitems(config, items):
     try:
         import torch
