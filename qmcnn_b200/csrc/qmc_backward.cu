@@ -15,7 +15,7 @@
 
 namespace qmc {
 
-// flat caller-order parameters -> padded block layout (the image c_params / shared memory hold)
+// flat caller-order parameters -> padded block layout (the image shared memory holds)
 __global__ void k_repack_params(DevModel m, const float* __restrict__ params, float* __restrict__ padded) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m.smem_param_floats) return;

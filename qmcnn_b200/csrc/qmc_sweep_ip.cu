@@ -22,8 +22,22 @@ constexpr int kIpAcc = 64;            // accumulators per lane
 // is (4096 chains on 148 x 12 slots would otherwise be 2.3 waves = 77% efficiency).
 struct IpSlice { long long task0, n_tasks, chunk_len; int group_warps, stagger; };
 
+// This file is compiled three times (Makefile): QMC_IP_PART 0 = the host side + k_sweep_ip<3> (phase groups, the default),
+// 1 = k_sweep_ip<0> (free-running, diagnosis), 2 = k_energy_ip.  Each kernel instantiates every register-tile shape of
+// the evaluator and takes about a minute of ptxas; three objects build in parallel.
+#ifndef QMC_IP_PART
+#define QMC_IP_PART 0
+#endif
+cudaError_t ip_launch_sweep_groups(int ctas, int threads, size_t smem, cudaStream_t st, const DevModel& m, const float* params,
+                                   const SweepArgs& a, const IpPlan& ip, const IpSlice& sl, const site_t* tab);
+cudaError_t ip_launch_sweep_free(int ctas, int threads, size_t smem, cudaStream_t st, const DevModel& m, const float* params,
+                                 const SweepArgs& a, const IpPlan& ip, const IpSlice& sl, const site_t* tab);
+cudaError_t ip_launch_energy(int grid, int threads, size_t smem, cudaStream_t st, const DevModel& m, const float* params,
+                             const int8_t* spins, int N, const float* cache, float2* partial, int nchunks, const IpPlan& ip,
+                             int group_warps, const site_t* tab);
+
 #if QMC_IP_PROFILE
-__device__ unsigned long long g_ip_prof[kIpProfPhases + 1 + 12];  // cycles per phase summed over warps, [8] = proposals,
+static __device__ unsigned long long g_ip_prof[kIpProfPhases + 1 + 12];  // cycles per phase summed over warps, [8] = proposals,
                                                                    // [9 + w] = task duration of warp w summed over CTAs
 #endif
 
@@ -53,6 +67,7 @@ __device__ __forceinline__ char* ip_cta_setup(float* after_params, const IpPlan&
 // bodies instead of twelve (the free-running version is instruction-fetch bound: 93% of the
 // GPC instruction-cache request rate, profiles/r01_summary.md).  Warps without a task or past
 // their chunk's end shadow a valid chain without writing anything, to keep barrier counts equal.
+#if QMC_IP_PART != 2
 template <int SYNC>
 __global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
 k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip, IpSlice sl,
@@ -232,6 +247,26 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
     if (a.n_accept && lane == 0 && accepted) atomicAdd(a.n_accept, accepted);
 }
 
+#if QMC_IP_PART == 0
+cudaError_t ip_launch_sweep_groups(int ctas, int threads, size_t smem, cudaStream_t st, const DevModel& m, const float* params,
+                                   const SweepArgs& a, const IpPlan& ip, const IpSlice& sl, const site_t* tab) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_ip<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_sweep_ip<3><<<ctas, threads, smem, st>>>(m, params, a, ip, sl, tab);
+    return cudaGetLastError();
+}
+#else
+cudaError_t ip_launch_sweep_free(int ctas, int threads, size_t smem, cudaStream_t st, const DevModel& m, const float* params,
+                                 const SweepArgs& a, const IpPlan& ip, const IpSlice& sl, const site_t* tab) {
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_ip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_sweep_ip<0><<<ctas, threads, smem, st>>>(m, params, a, ip, sl, tab);
+    return cudaGetLastError();
+}
+#endif
+#endif // QMC_IP_PART != 2
+
+#if QMC_IP_PART == 0
 // Is the model inside the in-place evaluator's coverage, and what does a warp need?
 IpPlan ip_plan(const qmc_handle* h) {
     IpPlan ip{};
@@ -377,9 +412,7 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
     const int sy = h->ip_sync;
     // two instances are built: free-running (QMC_IP_SYNC=0, diagnosis) and phase groups (default).  Per-proposal
     // group barriers (1) and CTA-wide per-layer barriers (2) were measured (profiles/r01_summary.md) and dropped.
-    auto kern = sy == 0 ? k_sweep_ip<0> : k_sweep_ip<3>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
     const long long slots = (long long)L.grid * L.warps;
     // time slicing: chunks of >= 64 steps, at most 64 chunks per chain; one chunk when S fits the slots
     long long chunks = 1;
@@ -399,11 +432,13 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
         const long long left = sl.n_tasks - sl.task0;
         const long long ctas = ((left < slots ? left : slots) + L.warps - 1) / L.warps;
         ++g_launches;
-        kern<<<(int)ctas, L.warps * 32, L.smem, st>>>(h->m, h->d_params_padded, a, L.ip, sl, h->d_ip_tab);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        e = (sy == 0 ? ip_launch_sweep_free : ip_launch_sweep_groups)((int)ctas, L.warps * 32, L.smem, st, h->m, h->d_params_padded,
+                                                                      a, L.ip, sl, h->d_ip_tab);
+        if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
+#endif // QMC_IP_PART == 0
 
 // ------------------------------------------------------------------------------------------------
 // k_energy_ip: TFIM local energies (ising_energy, mcmc_tf.py:59-90) with the same in-place evaluator.
@@ -413,6 +448,7 @@ cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLau
 // committed.  Phase-group barriers as in k_sweep_ip: every warp runs the same number of tasks and
 // sites, surplus ones shadow a valid evaluation without writing.
 // ------------------------------------------------------------------------------------------------
+#if QMC_IP_PART == 2
 __global__ void __launch_bounds__(kIpMaxWarps * 32, 1)
 k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restrict__ spins, int N,
             const float* __restrict__ cache_all, float2* __restrict__ partial, int nchunks, IpPlan ip,
@@ -466,6 +502,17 @@ k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restri
     }
 }
 
+cudaError_t ip_launch_energy(int grid, int threads, size_t smem, cudaStream_t st, const DevModel& m, const float* params,
+                             const int8_t* spins, int N, const float* cache, float2* partial, int nchunks, const IpPlan& ip,
+                             int group_warps, const site_t* tab) {
+    cudaError_t e = cudaFuncSetAttribute(k_energy_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_energy_ip<<<grid, threads, smem, st>>>(m, params, spins, N, cache, partial, nchunks, ip, group_warps, tab);
+    return cudaGetLastError();
+}
+#endif // QMC_IP_PART == 2
+
+#if QMC_IP_PART == 0
 // TFIM local energies through the in-place evaluator, if the model is inside its coverage
 bool energy_ip_supported(const qmc_handle* h) {
     if (!h->allow_ip) return false;
@@ -487,16 +534,15 @@ cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, co
     const long long need = (ntasks + w - 1) / w;
     const int grid = (int)(need < h->num_sms ? need : h->num_sms);
     const size_t smem = cta_bytes + (size_t)ip.per_warp_bytes * w;
-    cudaError_t e = cudaFuncSetAttribute(k_energy_ip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     ++g_launches;
-    k_energy_ip<<<grid, w * 32, smem, st>>>(h->m, h->d_params_padded, spins, N, cache, partial, nchunks, ip,
-                                            h->ip_group > 0 ? h->ip_group : 4, h->d_ip_tab);
-    return cudaGetLastError();
+    return ip_launch_energy(grid, w * 32, smem, st, h->m, h->d_params_padded, spins, N, cache, partial, nchunks, ip,
+                            h->ip_group > 0 ? h->ip_group : 4, h->d_ip_tab);
 }
+#endif // QMC_IP_PART == 0
 
 } // namespace qmc
 
+#if QMC_IP_PART == 0
 // phase cycles of k_sweep_ip since the last call (QMC_IP_PROFILE builds; zeros otherwise): out[0..7] cycles summed
 // over warps, out[8] proposals, out[9 + w] task duration of warp w of a CTA summed over CTAs and launches
 extern "C" int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/) {
@@ -516,3 +562,4 @@ extern "C" int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/)
 #endif
     return QMC_OK;
 }
+#endif // QMC_IP_PART == 0
