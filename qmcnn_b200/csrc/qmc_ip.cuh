@@ -141,6 +141,21 @@ __device__ __forceinline__ void ip_gather_frame(float4* arena4, const IpPlan& ip
     }
 }
 
+// The chain's lattice in shared memory, ONE BIT per spin (bit = spin up): 200 bytes instead of 1600 at 40 x 40, which is
+// what lets a 12th warp fit next to the weight block at C5 (11 warps before: 17.7 / 19.2 M proposals/s).
+__host__ __device__ inline int ip_spin_words(int n) { return (n + 31) >> 5; }
+__device__ __forceinline__ int ip_spin(const unsigned* spw, int site) { return ((spw[site >> 5] >> (site & 31)) & 1u) ? 1 : -1; }
+__device__ __forceinline__ void ip_pack_spins(unsigned* spw, const int8_t* __restrict__ g, int n, int lane) {
+    for (int base = 0; base < n; base += kWarp) {
+        const int i = base + lane;
+        const unsigned w = __ballot_sync(0xffffffffu, i < n && g[i] > 0);
+        if (lane == 0) spw[base >> 5] = w;
+    }
+}
+__device__ __forceinline__ void ip_unpack_spins(int8_t* __restrict__ g, const unsigned* spw, int n, int lane) {
+    for (int i = lane; i < n; i += kWarp) g[i] = ((spw[i >> 5] >> lane) & 1u) ? 1 : -1;     // i & 31 == lane
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Split-channel register tile.  conv_region_tiled gives a lane P sites x ALL output channels, so every weight is an
 // all-lane broadcast LDS.128 - two shared-memory wavefronts for 16 bytes - and the conv loops of k_sweep_ip were
@@ -375,7 +390,7 @@ __device__ __forceinline__ void ip_scatter_layer(const DevModel& m, const LayerI
 // nothing is staged (the cache is read-only), Re and Im are formed (dim).
 template <int ACC, int SYNC, bool SWEEP = true>
 __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPlan& ip, const float* sp,
-                                                  const unsigned* mg, float* arena, float* spt, const int8_t* spins_s,
+                                                  const unsigned* mg, float* arena, float* spt, const unsigned* spins_s,
                                                   const float* __restrict__ cache, float* staging,
                                                   int site_f, int lane, int gid, int gthreads, float& dre,
                                                   float* dim_out, const int* tabo, const site_t* tab_s,
@@ -392,7 +407,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
             const int ty = dtw.div(idx), tx = idx - ty * stw;
             const int site = wrap1(y0 - 2 * p + ty, Ly) * Lx + wrap1(x0 - 2 * p + tx, Lx);
             QMC_ASSERT(site >= 0 && site < n && idx < ip.spt_floats, "spin tile");
-            int s = spins_s[site];
+            int s = ip_spin(spins_s, site);
             if (site == site_f) s = -s;
             spt[idx] = (float)s;
         }

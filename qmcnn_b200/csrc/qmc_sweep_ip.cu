@@ -87,7 +87,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
     char* wmem = ip_cta_setup(smem_f + m.smem_param_floats, ip, tab_g, mg, tabo, tab_s) + (size_t)warp * ip.per_warp_bytes;
     float* arena = reinterpret_cast<float*>(wmem);
     float* spt = arena + ip.arena_floats;
-    int8_t* spins_s = reinterpret_cast<int8_t*>(spt + ip.spt_floats);
+    unsigned* spins_s = reinterpret_cast<unsigned*>(spt + ip.spt_floats);     // one bit per spin (ip_spin)
 
     const int n = m.n, p = m.p, Ly = m.Ly, Lx = m.Lx, D = m.D;
     const int slot = blockIdx.x * nwarps + warp;
@@ -112,7 +112,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
     {
         int8_t* gspins = a.spins + (size_t)chain * n;
         float* cache = a.cache + (size_t)chain * m.cache_floats;
-        for (int i = lane; i < n; i += kWarp) spins_s[i] = gspins[i];
+        ip_pack_spins(spins_s, gspins, n, lane);
         __syncwarp();
         const unsigned long long gchain = (unsigned long long)(a.chain_id0 + chain);
         // (flip site, uniform) of iteration `it`: Philox-4x32-10 keyed by (seed; step, global chain), or fed in
@@ -215,7 +215,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
                     const int y = dls.div(pos), x = pos - y * lside;
                     cache[m.fre_off + wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx)] = newf[pos];
                 }
-                if (lane == 0) spins_s[f0] = -spins_s[f0];
+                if (lane == 0) spins_s[f0 >> 5] ^= 1u << (f0 & 31);
                 __syncwarp();
                 ++accepted;
             }
@@ -228,7 +228,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
                 const long long j = (step - a.therm_its) / a.its_per_sample;
                 if (j < a.n_sample_slots) {
                     int8_t* dst = a.samples + ((size_t)j * a.S + chain) * n;
-                    for (int i = lane; i < n; i += kWarp) dst[i] = spins_s[i];
+                    ip_unpack_spins(dst, spins_s, n, lane);
                 }
             }
             prof.mark(7);
@@ -241,7 +241,7 @@ k_sweep_ip(DevModel m, const float* __restrict__ params, SweepArgs a, IpPlan ip,
         }
 #endif
         if (has_task)
-            for (int i = lane; i < n; i += kWarp) gspins[i] = spins_s[i];
+            ip_unpack_spins(gspins, spins_s, n, lane);
         __syncwarp();
     }
     if (a.n_accept && lane == 0 && accepted) atomicAdd(a.n_accept, accepted);
@@ -315,7 +315,7 @@ IpPlan ip_plan(const qmc_handle* h) {
     }
     ip.spt_floats = round4((1 + 4 * p) * (1 + 4 * p));
     ip.staging_floats = round4(staging);
-    ip.spins_bytes = (m.n + 15) & ~15;
+    ip.spins_bytes = (ip_spin_words(m.n) * 4 + 15) & ~15;          // one bit per spin
     ip.per_warp_bytes = (ip.arena_floats + ip.spt_floats) * 4 + ip.spins_bytes;
     ip.mg2p = fastdiv_magic(2 * p);
     ip.mg2p1 = fastdiv_magic(2 * p + 1);
@@ -463,7 +463,7 @@ k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restri
     char* wmem = ip_cta_setup(smem_f + m.smem_param_floats, ip, tab_g, mg, tabo, tab_s) + (size_t)warp * ip.per_warp_bytes;
     float* arena = reinterpret_cast<float*>(wmem);
     float* spt = arena + ip.arena_floats;
-    int8_t* spins_s = reinterpret_cast<int8_t*>(spt + ip.spt_floats);
+    unsigned* spins_s = reinterpret_cast<unsigned*>(spt + ip.spt_floats);     // one bit per spin (ip_spin)
     const int n = m.n;
     const int g = warp / group_warps, gid = 1 + g, gthreads = 32 * min(group_warps, nwarps - g * group_warps);
     const int cs = (n + nchunks - 1) / nchunks;
@@ -477,7 +477,7 @@ k_energy_ip(DevModel m, const float* __restrict__ params, const int8_t* __restri
         const int s = (int)(tt / nchunks), chunk = (int)(tt - (long long)s * nchunks);
         if (s != loaded) {
             __syncwarp();
-            for (int i = lane; i < n; i += kWarp) spins_s[i] = spins[(size_t)s * n + i];
+            ip_pack_spins(spins_s, spins + (size_t)s * n, n, lane);
             __syncwarp();
             loaded = s;
         }
