@@ -177,10 +177,14 @@ __device__ __forceinline__ void ip_unpack_spins(int8_t* __restrict__ g, const un
                               // (4 measured: fewer FFMA2, but 3 more tile bodies - no_instructions 5% -> 12%, 16.0 vs 19.8 M/s)
 #endif
 
-template <int K, int CIN, int COUT, int CS, int P, typename OutF, typename MidF>
+//   TA > 0: the tile's plane stride (float4 words) is this compile-time constant (the in-place arena: kIpPlane), so the
+//   second channel group of a pair is an immediate offset of the first one's address: one integer add per (site, tap,
+//   PAIR of channel groups) instead of ~3 per (site, tap, channel group) - they were 5% of k_sweep_ip's instructions.
+template <int K, int CIN, int COUT, int CS, int P, int TA = 0, typename OutF, typename MidF>
 __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const float* wsm, const float* tin, int tw,
                                                   int tarea, int side, int lane, OutF out, MidF mid,
                                                   const site_t* tab, int cap4 = 0x7fffffff) {
+    QMC_ASSERT(TA == 0 || TA == tarea, "compile-time plane stride");
     // cap4 (debug builds): float4 words of the input tile buffer - every input read is checked against it
     static_assert(CS == 2 || CS == 4, "channel parts");
     constexpr int CL = COUT / CS;             // output channels of this lane
@@ -190,11 +194,12 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
     // aligned lane quads hold two slots x two parts (lds_patterns.cu)
     const int part = CS == 2 ? (lane & 1) : ((lane >> 1) & 3);
     const int slot = CS == 2 ? (lane >> 1) : ((lane & 1) | ((lane >> 3) << 1));
-    // the lane's P input positions as pointers: one address add per (site, tap, channel group) in the loop below
-    const float4* pin[P];
+    // the lane's P input positions as shared-memory byte addresses; the (tap, channel group) part of an address is
+    // warp-uniform, so that the loads below can take the form LDS [R + UR] with no per-lane address arithmetic
+    unsigned pin[P];
     unsigned valid = 0;                       // bit j: site j of this slot is a real output
     {
-        const float4* tin4 = reinterpret_cast<const float4*>(tin);
+        const unsigned tin_a = smem_addr_u32(tin);
         const site_t first = tab[slot];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
@@ -203,7 +208,7 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
             else pk = first != kNoSite ? first : 0u;       // duplicate work, result discarded below
             QMC_ASSERT((int)(pk >> 16) == (int)((pk >> 8) & 255u) * tw + (int)(pk & 255u), "site table: offset = y * pitch + x");
             QMC_ASSERT((int)(pk >> 16) + (K - 1) * tw + (K - 1) + (NCG - 1) * tarea < cap4, "conv input window inside the tile buffer");
-            pin[j] = tin4 + (pk >> 16);
+            pin[j] = tin_a + (pk >> 16) * 16u;
         }
     }
     const int wlane = wbase + part * CL, blane = bbase + part * CL;
@@ -225,13 +230,10 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
         { const int v_ = *(volatile int*)&s_ip_conv[sched_]; ++conc_[v_ < 1 ? 0 : v_ > 4 ? 3 : v_ - 1]; }
 #endif
         const int dy = d / K, dx = d - dy * K;
-        const int toff = dy * tw + dx;
+        const unsigned toff = (unsigned)(dy * tw + dx) * 16u;
         const int wrow = wlane + d * CIN * COUT;
-#pragma unroll(kCgUnroll)
-        for (int cg = 0; cg < NCG; ++cg) {
-            float4 in[P];
-#pragma unroll
-            for (int j = 0; j < P; ++j) in[j] = pin[j][cg * tarea + toff];
+        // one channel group: four input channels of every site against this lane's CL output channels
+        auto fma_group = [&](int cg, const float4 (&in)[P]) {
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 float2 w[CL / 2];
@@ -248,6 +250,36 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
 #pragma unroll
                     for (int q2 = 0; q2 < CL / 2; ++q2) acc[j][q2] = __ffma2_rn(v2, w[q2], acc[j][q2]);
                 }
+            }
+        };
+        if constexpr (TA > 0 && NCG % 2 == 0) {
+#pragma unroll 1
+            for (int cp = 0; cp < NCG / 2; ++cp) {             // pairs of channel groups: the loop body of kCgUnroll = 2
+                unsigned a[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j) a[j] = pin[j] + toff + (unsigned)cp * (2u * TA * 16u);
+                float4 in0[P], in1[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(in0[j].x), "=f"(in0[j].y), "=f"(in0[j].z), "=f"(in0[j].w) : "r"(a[j]));
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                                 : "=f"(in1[j].x), "=f"(in1[j].y), "=f"(in1[j].z), "=f"(in1[j].w) : "r"(a[j]), "n"(TA * 16));
+                fma_group(2 * cp, in0);
+                fma_group(2 * cp + 1, in1);
+            }
+        } else {
+#pragma unroll(kCgUnroll)
+            for (int cg = 0; cg < NCG; ++cg) {
+                float4 in[P];
+                const unsigned uoff = toff + (unsigned)(cg * tarea) * 16u;          // warp-uniform
+#pragma unroll
+                for (int j = 0; j < P; ++j)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(in[j].x), "=f"(in[j].y), "=f"(in[j].z), "=f"(in[j].w) : "r"(pin[j] + uoff));
+                fma_group(cg, in);
             }
         }
     }
@@ -303,7 +335,7 @@ __host__ __device__ inline IpTile ip_tile(int acc, int cout, int npos) {
     return t;
 }
 
-template <int K, int CIN, int COUT, int ACC, typename OutF, typename MidF>
+template <int K, int CIN, int COUT, int ACC, int TA = 0, typename OutF, typename MidF>
 __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const float* wsm, const float* tin,
                                                     int tw, int tarea, int side, int lane, OutF out, MidF mid,
                                                     const site_t* tab, int cap4 = 0x7fffffff) {
@@ -311,13 +343,13 @@ __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const 
 #if QMC_IP_SPLIT
     constexpr int CL = COUT / 2;
     if constexpr (QMC_IP_SPLIT >= 4 && COUT == 16) {
-#define QMC_SPLIT4(PP) conv_region_split<K, CIN, COUT, 4, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
+#define QMC_SPLIT4(PP) conv_region_split<K, CIN, COUT, 4, (PP), TA>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
         if (npos <= 4 * 8) return QMC_SPLIT4(4);
         if (npos <= 7 * 8) return QMC_SPLIT4(7);
         if (npos <= 11 * 8) return QMC_SPLIT4(11);
 #undef QMC_SPLIT4
     }
-#define QMC_SPLIT(PP) conv_region_split<K, CIN, COUT, 2, (PP)>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
+#define QMC_SPLIT(PP) conv_region_split<K, CIN, COUT, 2, (PP), TA>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
     if (npos <= 2 * 16) return QMC_SPLIT(2);
     if (npos <= 4 * 16) return QMC_SPLIT(4);
     if (npos <= 6 * 16) return QMC_SPLIT(6);
@@ -476,9 +508,9 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                 ip_gather_frame(arena4, ip, plane, ncg, n, hn, p, mg[l], y0, x0, Ly, Lx, lane);
             };
             if (L.cin == 16 && L.cout == 16)
-                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab, cap4);
+                conv_region_pick_ip<3, 16, 16, ACC, kIpPlane>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab, cap4);
             else
-                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab, cap4);
+                conv_region_pick_ip<3, 8, 8, ACC, kIpPlane>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, mid, tab, cap4);
             stg += L.coutp * rarea;
             cp_async_wait_all();
         } else {
@@ -487,11 +519,11 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
                 arena4[cog * rarea + pos] = a;
             };
             if (L.cin == 16 && L.cout == 16)
-                conv_region_pick_ip<3, 16, 16, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
+                conv_region_pick_ip<3, 16, 16, ACC, kIpPlane>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
             else if (L.cin == 16 && L.cout == 8)
-                conv_region_pick_ip<3, 16, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
+                conv_region_pick_ip<3, 16, 8, ACC, kIpPlane>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
             else
-                conv_region_pick_ip<3, 8, 8, ACC>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
+                conv_region_pick_ip<3, 8, 8, ACC, kIpPlane>(L.sw_off, L.sb_off, sp, tin, T, TA, side, lane, out, sync, tab, cap4);
         }
         __syncwarp();
         prof.mark(5);

@@ -291,7 +291,8 @@ IpPlan ip_plan(const qmc_handle* h) {
     }
     if ((1 + 2 * m.D * p) * (1 + 2 * m.D * p) > 8 * kWarp) return ip;      // head: at most 8 sites per lane
     ip.T = 1 + 2 * (m.D + 1) * p;
-    ip.tarea = ip.T * ip.T;
+    if (ip.T * ip.T > kIpPlane) return ip;                                    // (cannot happen inside the coverage above)
+    ip.tarea = kIpPlane;
     ip.c = (m.D + 1) * p;
     const int lside = 1 + 2 * m.D * p, theta = m.layer[m.D - 1].coutp * lside * lside;
     int arena = ip.tarea * cmax;
