@@ -173,8 +173,9 @@ __device__ __forceinline__ void ip_unpack_spins(int8_t* __restrict__ g, const un
 //   tab: entry [j * NS + slot] = make_site(y, x, tile pitch) of the slot's j-th site or kNoSite, NS = 32 / CS slots.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef QMC_IP_SPLIT
-#define QMC_IP_SPLIT 2        // 0: one-part tiles (conv_region_tiled); 2: two channel parts; 4: four parts for small windows
-                              // (4 measured: fewer FFMA2, but 3 more tile bodies - no_instructions 5% -> 12%, 16.0 vs 19.8 M/s)
+#define QMC_IP_SPLIT 4        // 0: one-part tiles (conv_region_tiled); 2: two channel parts; 4: + four parts for the 7x7 and 9x9
+                              // windows (56 and 88 site slots instead of 64 and 96: 21.45 -> 21.99 M proposals/s).  Four parts
+                              // for the 5x5 window as well (same 32 slots, fewer weight loads) measured 16.0 vs 19.8: not used.
 #endif
 
 //   TA > 0: the tile's plane stride (float4 words) is this compile-time constant (the in-place arena: kIpPlane), so the
@@ -309,13 +310,13 @@ struct IpTile { int cs, p, ns; };
 __host__ __device__ inline IpTile ip_tile(int acc, int cout, int npos) {
     IpTile t;
 #if QMC_IP_SPLIT
-    // 16 output channels, windows up to 9x9: four channel parts x eight site slots (finer rounding of the window:
+    // 16 output channels, 7x7 and 9x9 windows: four channel parts x eight site slots (finer rounding of the window:
     // 56 instead of 64 site slots for 7x7, 88 instead of 96 for 9x9, and half the weight loads); else two parts
-    if (QMC_IP_SPLIT >= 4 && cout == 16 && npos <= 88) {
+    if (QMC_IP_SPLIT >= 4 && cout == 16 && npos > 32 && npos <= 88) {
         t.cs = 4;
         t.ns = kWarp / t.cs;
         const int need = (npos + t.ns - 1) / t.ns;
-        t.p = need <= 4 ? 4 : need <= 7 ? 7 : 11;
+        t.p = need <= 7 ? 7 : 11;
         return t;
     }
     t.cs = 2;
@@ -344,9 +345,8 @@ __device__ __forceinline__ void conv_region_pick_ip(int wbase, int bbase, const 
     constexpr int CL = COUT / 2;
     if constexpr (QMC_IP_SPLIT >= 4 && COUT == 16) {
 #define QMC_SPLIT4(PP) conv_region_split<K, CIN, COUT, 4, (PP), TA>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
-        if (npos <= 4 * 8) return QMC_SPLIT4(4);
-        if (npos <= 7 * 8) return QMC_SPLIT4(7);
-        if (npos <= 11 * 8) return QMC_SPLIT4(11);
+        if (npos > 32 && npos <= 7 * 8) return QMC_SPLIT4(7);
+        if (npos > 7 * 8 && npos <= 11 * 8) return QMC_SPLIT4(11);
 #undef QMC_SPLIT4
     }
 #define QMC_SPLIT(PP) conv_region_split<K, CIN, COUT, 2, (PP), TA>(wbase, bbase, wsm, tin, tw, tarea, side, lane, out, mid, tab, cap4)
