@@ -269,7 +269,7 @@ k_bwd_head(DevModel m, const float* __restrict__ params, const float2* __restric
     bwd_zero(sm.G, bp.plane_floats);
     bwd_bar_init(sm.bar);
     const unsigned bar_a = smem_addr_u32(sm.bar);
-    const site_t* tab = sm.tab + warp * bp.P * 16;
+    const site_t* tab = sm.tab + warp * (bp.P + 1) * 16;
     const int n = m.n, Ly = m.Ly, Lx = m.Lx, PW = bp.PW, PA = bp.PA, half = COUT / 2;
     const float* inoff = cache_all + m.layer[m.D - 2].act_off;
     unsigned phase = 0;
@@ -328,7 +328,7 @@ k_bwd_layer(DevModel m, int l, const float* __restrict__ params, int N, const fl
     bwd_zero(sm.G, bp.plane_floats);
     bwd_bar_init(sm.bar);
     const unsigned bar_a = smem_addr_u32(sm.bar);
-    const site_t* tab = sm.tab + warp * bp.P * 16;
+    const site_t* tab = sm.tab + warp * (bp.P + 1) * 16;
     const int n = m.n, Ly = m.Ly, Lx = m.Lx, PW = bp.PW, PA = bp.PA;
     const float* inoff = cache_all + m.layer[l - 1].act_off;
     unsigned phase = 0;
@@ -455,7 +455,7 @@ static BwdPlan bwd_plan(const qmc_handle* h) {
         if (BH * m.Lx > kBwdPlaneWarps * 6 * 16) continue;
         const int PA = (BH + 2) * bp.PW;
         const int plane = round4((PA + bp.PW) * cmax);
-        const size_t smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)plane + round4(9 * 16 * 16 + 16)) * 4 + sizeof(site_t) * kBwdPlaneWarps * 6 * 16;
+        const size_t smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)plane + round4(9 * 16 * 16 + 16)) * 4 + sizeof(site_t) * kBwdPlaneWarps * 7 * 16;
         if (smem > budget) continue;
         bp.BH = BH; bp.nbands = nb; bp.PA = PA; bp.plane_floats = plane;
         break;
@@ -474,7 +474,7 @@ static BwdPlan bwd_plan(const qmc_handle* h) {
         }
     if (best < 0) return bp;
     // the conv needs `warps`; the weight gradient likes all eight: tables cover 8 warps, surplus ones hold no sites
-    bp.tab_entries = (kBwdPlaneWarps * bp.P * 16 + 7) & ~7;
+    bp.tab_entries = (kBwdPlaneWarps * (bp.P + 1) * 16 + 7) & ~7;
     bp.gfloats = cmax * m.n;
     bp.smem = ((size_t)4 + round4(9 * 16 * 16 + 16) + 2 * (size_t)bp.plane_floats + round4(9 * 16 * 16 + 16)) * 4 + (size_t)bp.tab_entries * sizeof(site_t);
     (void)warps;
@@ -488,7 +488,7 @@ bool backward_plane_supported(const qmc_handle* h) { return bwd_plan(h).ok != 0;
 static void band_site_table(int s0, int s1, int Lx, int PW, int P, site_t* tab) {
     const int cnt = s1 > s0 ? s1 - s0 : 0, G = (cnt + P - 1) / P;
     std::vector<char> taken(cnt > 0 ? cnt : 1, 0);
-    for (int i = 0; i < P * 16; ++i) tab[i] = kNoSite;
+    for (int i = 0; i < (P + 1) * 16; ++i) tab[i] = kNoSite;
     int left = cnt;
     for (int j = 0; j < P; ++j)
         for (int h0 = 0; h0 < 16; h0 += 8) {
@@ -509,6 +509,7 @@ static void band_site_table(int s0, int s1, int Lx, int PW, int P, site_t* tab) 
                 tab[j * 16 + slot] = make_site(y, x, PW);
             }
         }
+    finish_site_table(tab, P, 16);
 }
 
 cudaError_t bwd_plane_upload_tables(qmc_handle* h) {
@@ -519,7 +520,7 @@ cudaError_t bwd_plane_upload_tables(qmc_handle* h) {
     const int bs = bp.BH * h->m.Lx;
     for (int w = 0; w < kBwdPlaneWarps; ++w) {
         const int s0 = w * bp.chunk < bs ? w * bp.chunk : bs, s1 = s0 + bp.chunk < bs ? s0 + bp.chunk : bs;
-        band_site_table(s0, s1, h->m.Lx, bp.PW, bp.P, tab.data() + (size_t)w * bp.P * 16);
+        band_site_table(s0, s1, h->m.Lx, bp.PW, bp.P, tab.data() + (size_t)w * (bp.P + 1) * 16);
     }
     cudaError_t e = cudaMalloc(&h->d_bwd_tab, tab.size() * sizeof(site_t));
     if (e != cudaSuccess) return e;

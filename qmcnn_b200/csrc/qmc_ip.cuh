@@ -170,7 +170,7 @@ __device__ __forceinline__ void ip_unpack_spins(int8_t* __restrict__ g, const un
 // Per (tap, 4 input channels): 8 x 2 + 2P x 2 wavefronts instead of 16 x 2 + P x 4 (P = sites per lane before): 20 / 24
 // / 28 / 32 instead of 36 / 40 / 44 / 48 for the 5x5 ... 11x11 windows.  The fma chain of an output value is unchanged
 // (bias, taps ascending, input channels ascending), so results stay bit-identical.
-//   tab: entry [j * NS + slot] = make_site(y, x, tile pitch) of the slot's j-th site or kNoSite, NS = 32 / CS slots.
+//   tab: P rows of NS = 32 / CS entries make_site(y, x, tile pitch) + one row of valid masks (qmc_device.cuh: site_t).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef QMC_IP_SPLIT
 #define QMC_IP_SPLIT 4        // 0: one-part tiles (conv_region_tiled); 2: two channel parts; 4: + four parts for the 7x7 and 9x9
@@ -201,15 +201,13 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
     unsigned valid = 0;                       // bit j: site j of this slot is a real output
     {
         const unsigned tin_a = smem_addr_u32(tin);
-        const site_t first = tab[slot];
+        valid = tab[P * NS + slot];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
-            site_t pk = tab[j * NS + slot];
-            if (pk != kNoSite) valid |= 1u << j;
-            else pk = first != kNoSite ? first : 0u;       // duplicate work, result discarded below
-            QMC_ASSERT((int)(pk >> 16) == (int)((pk >> 8) & 255u) * tw + (int)(pk & 255u), "site table: offset = y * pitch + x");
-            QMC_ASSERT((int)(pk >> 16) + (K - 1) * tw + (K - 1) + (NCG - 1) * tarea < cap4, "conv input window inside the tile buffer");
-            pin[j] = tin_a + (pk >> 16) * 16u;
+            const site_t pk = tab[j * NS + slot];
+            QMC_ASSERT((int)(pk >> 16) == ((int)((pk >> 8) & 255u) * tw + (int)(pk & 255u)) * 16, "site table: offset = (y * pitch + x) * 16");
+            QMC_ASSERT((int)(pk >> 20) + (K - 1) * tw + (K - 1) + (NCG - 1) * tarea < cap4, "conv input window inside the tile buffer");
+            pin[j] = tin_a + (pk >> 16);
         }
     }
     const int wlane = wbase + part * CL, blane = bbase + part * CL;
@@ -218,12 +216,16 @@ __device__ __forceinline__ void conv_region_split(int wbase, int bbase, const fl
     int conc_[4] = {0, 0, 0, 0};
     if (lane == 0) atomicAdd(&s_ip_conv[sched_], 1);
 #endif
+    // accumulators start from the bias: one broadcast load per accumulator pair instead of one load and P register moves
+    // per pair (64 MOVs for the 8-site tile)
     float2 acc[P][CL / 2];
+    {
+        const unsigned b_a = smem_addr_u32(wsm + blane);
 #pragma unroll
-    for (int q2 = 0; q2 < CL / 2; ++q2) {
-        const float2 b = *reinterpret_cast<const float2*>(wsm + blane + 2 * q2);
+        for (int j = 0; j < P; ++j)
 #pragma unroll
-        for (int j = 0; j < P; ++j) acc[j][q2] = b;
+            for (int q2 = 0; q2 < CL / 2; ++q2)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(acc[j][q2].x), "=f"(acc[j][q2].y) : "r"(b_a + 8u * q2));
     }
 #pragma unroll 1
     for (int d = 0; d < K * K; ++d) {

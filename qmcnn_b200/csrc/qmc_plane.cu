@@ -70,7 +70,7 @@ k_forward_plane(DevModel m, const float* __restrict__ params, const int8_t* __re
     load_params_to_smem(m, params, sp);
     for (int i = tid; i < pp.tab_entries; i += nthr) tab_s[i] = tab_g[i];
     __syncthreads();
-    const site_t* tab = tab_s + warp * pp.P * 16;
+    const site_t* tab = tab_s + warp * (pp.P + 1) * 16;
 
     const int p = m.p, Ly = m.Ly, Lx = m.Lx, n = m.n, D = m.D, PW = pp.PW, PA = pp.PA;
     const FastDiv dPW(PW), dLx(Lx), dn(n);
@@ -171,7 +171,7 @@ k_forward_plane(DevModel m, const float* __restrict__ params, const int8_t* __re
 static void plane_site_table(int s0, int s1, int Lx, int PW, int P, site_t* tab) {
     const int cnt = s1 - s0, G = (cnt + P - 1) / P;
     std::vector<char> taken(cnt > 0 ? cnt : 1, 0);
-    for (int i = 0; i < P * 16; ++i) tab[i] = kNoSite;
+    for (int i = 0; i < (P + 1) * 16; ++i) tab[i] = kNoSite;
     int left = cnt;
     for (int j = 0; j < P; ++j)
         for (int h0 = 0; h0 < 16; h0 += 8) {
@@ -192,6 +192,7 @@ static void plane_site_table(int s0, int s1, int Lx, int PW, int P, site_t* tab)
                 tab[j * 16 + slot] = make_site(y, x, PW);
             }
         }
+    finish_site_table(tab, P, 16);
 }
 
 static PlanePlan plane_plan(const qmc_handle* h) {
@@ -223,7 +224,7 @@ static PlanePlan plane_plan(const qmc_handle* h) {
             break;                                                  // the smallest w that fits this P
         }
     if (best < 0 || m.n * 4 > 65535) return pp;                     // more than 8 x 96 sites: k_forward
-    pp.tab_entries = (pp.warps * pp.P * 16 + 7) & ~7;
+    pp.tab_entries = (pp.warps * (pp.P + 1) * 16 + 7) & ~7;
     pp.smem = ((size_t)m.smem_param_floats + 2 * (size_t)pp.plane_floats + round4(pp.PA) + 64) * 4 + (size_t)pp.tab_entries * sizeof(site_t);
     if (pp.smem > h->max_smem) return pp;
     pp.ok = 1;
@@ -240,7 +241,7 @@ cudaError_t plane_upload_tables(qmc_handle* h) {
     std::vector<site_t> tab(pp.tab_entries, kNoSite);
     for (int w = 0; w < pp.warps; ++w) {
         const int s0 = w * pp.chunk, s1 = s0 + pp.chunk < h->m.n ? s0 + pp.chunk : h->m.n;
-        plane_site_table(s0 < h->m.n ? s0 : h->m.n, s1, h->m.Lx, pp.PW, pp.P, tab.data() + (size_t)w * pp.P * 16);
+        plane_site_table(s0 < h->m.n ? s0 : h->m.n, s1, h->m.Lx, pp.PW, pp.P, tab.data() + (size_t)w * (pp.P + 1) * 16);
     }
     cudaError_t e = cudaMalloc(&h->d_plane_tab, tab.size() * sizeof(site_t));
     if (e != cudaSuccess) return e;

@@ -328,7 +328,7 @@ IpPlan ip_plan(const qmc_handle* h) {
         const int side = 1 + 2 * (l + 1) * p;
         ip.tab_off[l] = entries;
         const IpTile t = ip_tile(kIpAcc, m.layer[l].cout, side * side);
-        entries += t.p * t.ns;
+        entries += (t.p + 1) * t.ns;
     }
     ip.tab_entries = (entries + 7) & ~7;
     ip.ok = 1;
@@ -344,7 +344,7 @@ IpPlan ip_plan(const qmc_handle* h) {
 static void ip_site_table(int side, int T, int P, int NS, bool conflict_free, site_t* tab) {
     const int npos = side * side, G = (npos + P - 1) / P;
     std::vector<char> taken(npos, 0);
-    for (int i = 0; i < P * NS; ++i) tab[i] = kNoSite;
+    for (int i = 0; i < (P + 1) * NS; ++i) tab[i] = kNoSite;
     int left = npos;
     for (int j = 0; j < P; ++j)
         for (int s0 = 0; s0 < NS; s0 += 8) {
@@ -365,6 +365,7 @@ static void ip_site_table(int side, int T, int P, int NS, bool conflict_free, si
                 tab[j * NS + slot] = make_site(y, x, T);
             }
         }
+    finish_site_table(tab, P, NS);
 }
 
 // device image of the site tables of a handle (built once, qmc_create)
