@@ -57,7 +57,14 @@ static __device__ __noinline__ float4 ip_tanh4_any(float4 a) {
     return a;
 }
 
+#ifndef QMC_IP_TANH_INLINE
+#define QMC_IP_TANH_INLINE 0      // 1: the small-argument path inlined at every call site (variant build; measured, profiles/r02_summary.md)
+#endif
+#if QMC_IP_TANH_INLINE
+__device__ __forceinline__ float4 ip_tanh4(float4 a) {
+#else
 static __device__ __noinline__ float4 ip_tanh4(float4 a) {
+#endif
     const float mx = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
     if (!(mx < kTanhSmall)) return ip_tanh4_any(a);          // (NaN goes to tanhf too)
     a.x = tanh_small(a.x); a.y = tanh_small(a.y); a.z = tanh_small(a.z); a.w = tanh_small(a.w);
