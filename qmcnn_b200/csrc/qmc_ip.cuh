@@ -36,27 +36,7 @@ struct IpProf {
 // once per proposal must be compact: 64 inlined tanhf per register tile were 18 KB per tile shape
 // and the first version of this kernel stalled 34% of its cycles on instruction fetch.  Same
 // library tanhf / log2cosh_c as every other path, so the results stay bit-identical.
-// tanhf's own small-argument branch, instruction for instruction (CUDA 12.9 libdevice, |x| < 0.6: an odd polynomial,
-// x + x * (x^2 * p(x^2)), five fma and a mul in this order with these constants) - bit-identical to tanhf there
-// (checked over every float by qmc_diag_tanh_check, tests/test_gpu_parity.py).  tanhf itself evaluates BOTH branches
-// (ex2 / rcp and the polynomial) and selects: 16 instructions per value.  The hidden activations of a window are small
-// almost always, so ip_tanh4 takes this 6-instruction path when all four values of the lane are below the threshold
-// and calls tanhf otherwise: 4560 tanh per proposal were 8.5% of k_sweep_ip's instructions.
-__device__ __forceinline__ float tanh_small(float x) {
-    const float x2 = x * x;
-    float p = fmaf(x2, __int_as_float(0x3C80F082), __int_as_float(0xBD563CAE));
-    p = fmaf(p, x2, __int_as_float(0x3E085941));
-    p = fmaf(p, x2, __int_as_float(0xBEAAA9ED));
-    p = fmaf(p, x2, 0.f);
-    return fmaf(p, x, x);
-}
-constexpr float kTanhSmall = 0.60000002384185791016f;      // 0x3F19999A, tanhf's branch point
-
-static __device__ __noinline__ float4 ip_tanh4_any(float4 a) {
-    a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w);
-    return a;
-}
-
+// (tanh_small / kTanhSmall / ip_tanh4_any: qmc_device.cuh - the classic evaluator uses the same fast path)
 #ifndef QMC_IP_TANH_INLINE
 #define QMC_IP_TANH_INLINE 0      // 1: the small-argument path inlined at every call site (variant build; measured, profiles/r02_summary.md)
 #endif

@@ -12,8 +12,11 @@
 // executed inside the step loop.
 #include "qmc_host.h"
 
-// Compiled twice (Makefile): QMC_MAXW=8 (<= 8 warps per CTA, 255 registers, big register
-// tiles - the large-model variant) and QMC_MAXW=16 (128 registers, small models).
+// Compiled three times (Makefile): QMC_MAXW=8 (<= 8 warps per CTA, 255 registers, big register
+// tiles - the large-model variant), QMC_MAXW=16 (128 registers, small models) and QMC_MAXW=28
+// (72 registers, 7 warps per scheduler: models with <= 8 channels per layer, whose proposals
+// are a few thousand instructions of mostly latency - C2: 4096 chains are ONE wave of 148 x 28
+// warps, 135 -> 168 M proposals/s, profiles/r02_small_configs.md).
 #ifndef QMC_MAXW
 #define QMC_MAXW 8
 #endif
@@ -256,17 +259,19 @@ k_sweep_sym(DevModel m, const float* __restrict__ sym_padded, SweepArgs a, EvalP
                             const LayerInfo& L = m.layer[l];
                             const int rarea = rh * rw, ncg = L.coutp >> 2;
                             float4* plane4 = reinterpret_cast<float4*>(cache + L.act_off);
+                            const FastDiv drw(rw), darea(rarea);
                             for (int idx = lane; idx < ncg * rarea; idx += kWarp) {
-                                const int cg = idx / rarea, pos = idx - cg * rarea;
-                                const int y = pos / rw, x = pos - y * rw;
+                                const int cg = darea.div(idx), pos = idx - cg * rarea;
+                                const int y = drw.div(pos), x = pos - y * rw;
                                 plane4[cg * n + wrap1(ry + y, Ly) * Lx + wrap1(rx + x, Lx)] =
                                     ldcg4(stg_g + stg + (size_t)idx * 4);
                             }
                             stg += L.coutp * rarea;
                             ry -= p; rx -= p; rh += 2 * p; rw += 2 * p;
                         }
+                        const FastDiv dregw(reg.rw);
                         for (int pos = lane; pos < reg.rh * reg.rw; pos += kWarp) {
-                            const int y = pos / reg.rw, x = pos - y * reg.rw;
+                            const int y = dregw.div(pos), x = pos - y * reg.rw;
                             const int site = wrap1(reg.ry + y, Ly) * Lx + wrap1(reg.rx + x, Lx);
                             cache[m.fre_off + site] = nf[pos];
                             cache[m.fim_off + site] = nf[pl.nfstride + pos];
@@ -336,6 +341,16 @@ cudaError_t launch_sweep_sym(const qmc_handle* h, const SweepArgs& a, int nsym, 
 #if QMC_MAXW == 8
 cudaError_t launch_sweep_w16(const qmc_handle* h, const SweepArgs& a, const EvalPlan& pl,
                              const WarpGrid& g, cudaStream_t st);
+cudaError_t launch_sweep_w28(const qmc_handle* h, const SweepArgs& a, const EvalPlan& pl,
+                             const WarpGrid& g, cudaStream_t st);
+
+// every layer has <= 8 output channels: the register tiles need <= 32 accumulators per lane and the
+// kernel fits 72 registers (the 28-warp object) without spilling its loops
+static bool narrow_model(const DevModel& m) {
+    for (int l = 0; l < m.D; ++l)
+        if (m.layer[l].cout > 8) return false;
+    return true;
+}
 
 int sweep_slots(const qmc_handle* h, int S, int num_flips, EvalPlan* plan, WarpGrid* grid) {
     const DevModel& m = h->m;
@@ -343,7 +358,7 @@ int sweep_slots(const qmc_handle* h, int S, int num_flips, EvalPlan* plan, WarpG
     if (num_flips > 1) { h0 = m.Ly / 2 + 1; w0 = m.Lx / 2 + 1; }
     if (!box_supported(m, h0, w0)) return -1;
     EvalPlan pl = eval_plan(m, h0, w0, false);
-    WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, S);
+    WarpGrid g = pick_warp_grid(h, pl.per_warp_bytes, 0, S, narrow_model(m) ? 28 : 16);
     if (!g.ok) return -2;
     if (plan) *plan = pl;
     if (grid) *grid = g;
@@ -355,7 +370,8 @@ cudaError_t launch_sweep(const qmc_handle* h, const SweepArgs& a, cudaStream_t s
     const int slots = sweep_slots(h, a.S, a.num_flips, &pl, &g);
     if (slots == -1) { err = "sweep: flip box does not fit the lattice (need h0 + r - 1 <= L for deep models)"; return cudaErrorInvalidValue; }
     if (slots < 0) { err = "sweep: model does not fit in shared memory"; return cudaErrorInvalidValue; }
-    return g.warps <= 8 ? launch_sweep_w8(h, a, pl, g, st) : launch_sweep_w16(h, a, pl, g, st);
+    return g.warps <= 8 ? launch_sweep_w8(h, a, pl, g, st)
+         : g.warps <= 16 ? launch_sweep_w16(h, a, pl, g, st) : launch_sweep_w28(h, a, pl, g, st);
 }
 #endif
 

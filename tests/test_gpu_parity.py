@@ -716,3 +716,33 @@ def test_tanh_fast_path_is_bit_identical_to_tanhf_for_every_float():
     bad = ctypes.c_ulonglong(123)
     assert q._lib.load().qmc_diag_tanh_check(0, ctypes.byref(bad)) == 0
     assert bad.value == 0
+
+
+@pytest.mark.parametrize("kind,kw,shape,S,flips", [("dcrbm", dict(layers=[8, 8, 8]), (10, 10), 4096, 1),
+                                                   ("crbm", dict(k=5, alpha=4), (6, 6), 64, 1),
+                                                   ("crbm", dict(k=3, alpha=2), (8, 8), 3000, 2)])
+def test_classic_sweep_launch_geometries_are_bit_identical(kind, kw, shape, S, flips):
+    """The classic persistent kernel is launched as k_sweep_w28 (models with <= 8 channels per layer: up to 28 warps per
+    CTA, 72 registers), k_sweep_w16 or k_sweep_w8, and fewer chains than SMs x warps are spread one warp per CTA
+    (pick_warp_grid).  Every geometry runs the same per-chain arithmetic: decisions, log-ratios, states and samples
+    must agree bit for bit with the launches capped at 16 and at 8 warps per CTA (tuning max_warps)."""
+    from gpu_util import make_pair
+    q = _q()
+    outs = []
+    for cap in (0, 16, 8):
+        gm, _ = make_pair(kind, shape[0], 2e-1, 57, **kw)
+        gm.tuning = dict(flags=q.FLAG_SWEEP_CLASSIC)
+        if cap:
+            gm.tuning["max_warps"] = cap
+        GS = type("GS", (q.Sampler,), dict(MAX_NUM_SAMPLERS=S, SWEEPFACTOR=1, THERMFACTOR=1))
+        init = (np.random.default_rng(9).integers(0, 2, (S,) + tuple(shape)) * 2 - 1).astype(np.int32)
+        smp = GS(gm, shape, gm.r, 2 * S, flips, seed=5, chain_id0=77)
+        smp.feed(initial_states=init)
+        samples = smp.mcmc_op(trace=True)
+        outs.append((smp.accept_trace.clone(), smp.logratio_trace.clone(), smp.spins.clone(), samples.clone(),
+                     smp.acceptance_count))
+    for b in outs[1:]:
+        a = outs[0]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "decisions / log-ratios differ"
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and a[4] == b[4]
+    assert 0 < outs[0][4] < outs[0][0].numel()
