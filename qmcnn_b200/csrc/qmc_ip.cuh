@@ -159,6 +159,12 @@ __device__ __forceinline__ void ip_unpack_spins(int8_t* __restrict__ g, const un
 // (bias, taps ascending, input channels ascending), so results stay bit-identical.
 //   tab: P rows of NS = 32 / CS entries make_site(y, x, tile pitch) + one row of valid masks (qmc_device.cuh: site_t).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef QMC_IP_L0_FASTDIV
+#define QMC_IP_L0_FASTDIV 0   // layer 0 (generic conv over the 3x3 window): site decode by integer division (0) or FastDiv (1).
+                              // The FastDiv form executes fewer instructions and measured 0.32% SLOWER (22.336 vs 22.407 M proposals/s,
+                              // twice each, alternating: profiles/r02_summary.md) - register allocation and code layout of the whole
+                              // kernel move with it (145 vs 149 registers)
+#endif
 #ifndef QMC_IP_SPLIT
 #define QMC_IP_SPLIT 4        // 0: one-part tiles (conv_region_tiled); 2: two channel parts; 4: + four parts for the 7x7 and 9x9
                               // windows (56 and 88 site slots instead of 64 and 96: 21.45 -> 21.99 M proposals/s).  Four parts
@@ -446,7 +452,7 @@ __device__ __forceinline__ void warp_eval_flip_ip(const DevModel& m, const IpPla
         const LayerInfo& L = m.layer[0];
         const int side = 1 + 2 * p, rarea = side * side, o0 = c - p;
         float4* stg4 = reinterpret_cast<float4*>(staging);
-        conv_region_generic(L, m.k, sp, spt, stw, stw * stw, side, side, lane,
+        conv_region_generic<QMC_IP_L0_FASTDIV != 0>(L, m.k, sp, spt, stw, stw * stw, side, side, lane,
                             [&](int pos, int y, int x, int cog, float4 a) {
                                 a = ip_tanh4(a);
                                 QMC_ASSERT((cog * TA + (y + o0) * T + (x + o0)) * 4 + 3 < ip.arena_floats && y + o0 < T && x + o0 < T,

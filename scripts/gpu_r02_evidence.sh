@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
 # full captures (one launch each) on the short profiling command: one full wave of 148 x 12 chains
 CMD="python bench.py --steps 1 --warmup 1 --sweep-its 100 --chains 1776 --no-cpu-baseline"
 $CMD > gpurun_out/plain_prof_$TAG.log 2>&1 || exit 1
-for k in k_sweep_ip:1 k_energy_ip:0 k_forward_plane:1 k_bwd_layerILi16ELi16:1 k_bwd_head:0; do
+for k in ${KERNELS:-k_sweep_ip:1 k_energy_ip:0 k_forward_plane:1 k_bwd_layerILi16ELi16:1 k_bwd_head:0}; do
   name=${k%%:*}; skip=${k#*:}
   ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -o gpurun_out/${name}_$TAG -f $CMD > gpurun_out/ncu_full_${name}_$TAG.log 2>&1
 done
