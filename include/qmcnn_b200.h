@@ -249,6 +249,20 @@ int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/);
  * bit-level mismatches (must be 0). */
 int qmc_diag_tanh_check(int device, unsigned long long* mismatches /*host*/);
 
+/* Host-only (no CUDA call, works without a GPU): the launch qmc_metropolis_sweep would make for this model / lattice /
+ * S chains / n_steps on a device with num_sms SMs and max_smem bytes of opt-in shared memory per CTA - the planner
+ * behind Sampler.mcmc_op (sampler.py:158-177) as a testable function.  out[0] = kernel (QMC_PLAN_*), out[1] = CTAs,
+ * out[2] = warps per CTA, out[3] = dynamic shared memory per CTA (bytes), out[4] = kernel launches for the n_steps,
+ * out[5] = steps per task (the chunk length of the time-sliced in-place kernel; n_steps otherwise), out[6] = warp slots,
+ * out[7] = 0.  QMC_PLAN_NONE: outside the incremental kernels' coverage (the Python Sampler then runs qmc_nd_sweep). */
+#define QMC_PLAN_NONE (-1)
+#define QMC_PLAN_SWEEP_W8 0   /* classic persistent kernel, <= 8 warps per CTA (255 registers) */
+#define QMC_PLAN_SWEEP_W16 1  /* ... <= 16 warps (128 registers) */
+#define QMC_PLAN_SWEEP_W28 2  /* ... <= 28 warps (72 registers; models with <= 8 channels per layer) */
+#define QMC_PLAN_SWEEP_IP 3   /* in-place, time-sliced persistent kernel (k_sweep_ip) */
+int qmc_diag_sweep_plan(const qmc_model_desc* desc, int S, int num_flips, int64_t n_steps, int num_sms, size_t max_smem,
+                        int64_t* out /*host, 8 entries*/);
+
 /* number of CUDA kernels this library has launched in this process (graph replays count
  * their kernel nodes) */
 unsigned long long qmc_launch_count(void);

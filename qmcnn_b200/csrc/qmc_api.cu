@@ -59,6 +59,27 @@ static bool build_model(const qmc_model_desc* d, DevModel& m, std::string& err) 
     return true;
 }
 
+// tuning / cross-check knobs (include/qmcnn_b200.h: qmc_model_desc.reserved)
+static void apply_tuning(qmc_handle* h, const qmc_model_desc* desc) {
+    const int flags = desc->reserved[0];
+    h->allow_tiled = !(flags & QMC_FLAG_GENERIC_CONV);
+    h->allow_ip = !(flags & QMC_FLAG_SWEEP_CLASSIC);
+    h->force_ip = (flags & QMC_FLAG_SWEEP_INPLACE) != 0;
+    h->ip_sync = (flags & QMC_FLAG_IP_FREE_RUNNING) ? 0 : 3;
+    h->ip_cf = !(flags & QMC_FLAG_IP_ROWMAJOR_SITES);
+    h->energy_path = (flags & QMC_FLAG_ENERGY_CLASSIC) ? 1 : (flags & QMC_FLAG_ENERGY_INPLACE) ? 2 : 0;
+    h->backward_generic = (flags & QMC_FLAG_BACKWARD_GENERIC) != 0;
+    h->forward_blocked = (flags & QMC_FLAG_FORWARD_BLOCKED) != 0;
+    h->backward_smem_only = (flags & QMC_FLAG_BACKWARD_SMEM) != 0;
+    h->max_warps_override = desc->reserved[1] > 0 ? desc->reserved[1] : 0;
+    h->ip_group = (desc->reserved[2] & 0xFF) > 0 ? (desc->reserved[2] & 0xFF) : 4;
+    {   // phase-group start offset of k_sweep_ip in units of 1024 cycles: 0 = default (40), 0xFFFF = none
+        const int st = (desc->reserved[2] >> 8) & 0xFFFF;
+        h->ip_stagger = st == 0 ? 40 : st == 0xFFFF ? 0 : st;
+    }
+    h->ip_chunks = desc->reserved[3] > 0 ? desc->reserved[3] : 64;
+}
+
 // fresh lattices: one Philox block = 128 spins (oracle/philox.py: initial_spins)
 __global__ void k_init_spins(int8_t* __restrict__ spins, int S, int n, unsigned long long seed, long long chain_id0,
                              unsigned reset_word) {
@@ -95,6 +116,35 @@ int qmc_init_spins(int device, int8_t* spins, int S, int n, uint64_t seed, int64
     return e == cudaSuccess ? QMC_OK : cuda_fail(nullptr, e, "init_spins");
 }
 
+int qmc_diag_sweep_plan(const qmc_model_desc* desc, int S, int num_flips, int64_t n_steps, int num_sms, size_t max_smem,
+                        int64_t* out) {
+    if (!desc || !out || S < 1 || n_steps < 1 || num_sms < 1) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "sweep_plan: bad argument");
+    if (num_flips < 1 || num_flips > QMC_MAX_FLIPS) return fail(nullptr, QMC_ERR_UNSUPPORTED, "sweep_plan: num_flips must be 1 or 2");
+    qmc_handle h;                        // host-only image of a handle: no CUDA call below
+    std::string err;
+    if (!build_model(desc, h.m, err)) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, err);
+    h.desc = *desc;
+    h.num_sms = num_sms;
+    h.max_smem = max_smem;
+    apply_tuning(&h, desc);
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if ((size_t)h.m.smem_param_floats * 4 > max_smem) return fail(nullptr, QMC_ERR_UNSUPPORTED, "parameters do not fit in shared memory");
+    IpLaunch il{};
+    if (num_flips == 1 && (il = ip_launch_plan(&h, S)).ok) {
+        long long launches = 0, chunk = 0;
+        ip_slice_counts(&h, il, S, n_steps, &launches, &chunk);
+        out[0] = QMC_PLAN_SWEEP_IP; out[1] = il.grid; out[2] = il.warps; out[3] = (int64_t)il.smem;
+        out[4] = launches; out[5] = chunk; out[6] = (int64_t)il.grid * il.warps;
+        return QMC_OK;
+    }
+    EvalPlan pl; WarpGrid g;
+    const int slots = sweep_slots(&h, S, num_flips, &pl, &g);
+    if (slots < 0) { out[0] = QMC_PLAN_NONE; return QMC_OK; }     // Sampler falls through to qmc_nd_sweep
+    out[0] = g.warps <= 8 ? QMC_PLAN_SWEEP_W8 : g.warps <= 16 ? QMC_PLAN_SWEEP_W16 : QMC_PLAN_SWEEP_W28;
+    out[1] = g.grid; out[2] = g.warps; out[3] = (int64_t)g.smem; out[4] = 1; out[5] = n_steps; out[6] = slots;
+    return QMC_OK;
+}
+
 const char* qmc_version(void) {
 #if QMC_DEBUG
     return "qmcnn_b200 0.2 (sm_100a, DEBUG build: device-side bounds checks)";
@@ -125,24 +175,7 @@ int qmc_create(qmc_handle** out, int device, const qmc_model_desc* desc) {
     cudaGetDeviceProperties(&prop, device);
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = prop.sharedMemPerBlockOptin;
-    // tuning / cross-check knobs (include/qmcnn_b200.h: qmc_model_desc.reserved)
-    const int flags = desc->reserved[0];
-    h->allow_tiled = !(flags & QMC_FLAG_GENERIC_CONV);
-    h->allow_ip = !(flags & QMC_FLAG_SWEEP_CLASSIC);
-    h->force_ip = (flags & QMC_FLAG_SWEEP_INPLACE) != 0;
-    h->ip_sync = (flags & QMC_FLAG_IP_FREE_RUNNING) ? 0 : 3;
-    h->ip_cf = !(flags & QMC_FLAG_IP_ROWMAJOR_SITES);
-    h->energy_path = (flags & QMC_FLAG_ENERGY_CLASSIC) ? 1 : (flags & QMC_FLAG_ENERGY_INPLACE) ? 2 : 0;
-    h->backward_generic = (flags & QMC_FLAG_BACKWARD_GENERIC) != 0;
-    h->forward_blocked = (flags & QMC_FLAG_FORWARD_BLOCKED) != 0;
-    h->backward_smem_only = (flags & QMC_FLAG_BACKWARD_SMEM) != 0;
-    h->max_warps_override = desc->reserved[1] > 0 ? desc->reserved[1] : 0;
-    h->ip_group = (desc->reserved[2] & 0xFF) > 0 ? (desc->reserved[2] & 0xFF) : 4;
-    {   // phase-group start offset of k_sweep_ip in units of 1024 cycles: 0 = default (40), 0xFFFF = none
-        const int st = (desc->reserved[2] >> 8) & 0xFFFF;
-        h->ip_stagger = st == 0 ? 40 : st == 0xFFFF ? 0 : st;
-    }
-    h->ip_chunks = desc->reserved[3] > 0 ? desc->reserved[3] : 64;
+    apply_tuning(h, desc);
     e = cudaMalloc(&h->d_params, sizeof(float) * (size_t)m.P);
     if (e == cudaSuccess) e = cudaMemset(h->d_params, 0, sizeof(float) * (size_t)m.P);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_params_padded, sizeof(float) * (size_t)m.smem_param_floats);

@@ -162,6 +162,8 @@ IpPlan ip_plan(const qmc_handle* h);
 cudaError_t ip_upload_tables(qmc_handle* h);
 IpLaunch ip_launch_plan(const qmc_handle* h, int S);
 cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st);
+// launches and steps per chunk of the time-sliced in-place sweep (host only; qmc_diag_sweep_plan)
+void ip_slice_counts(const qmc_handle* h, const IpLaunch& L, int S, long long n_steps, long long* launches, long long* chunk_len);
 bool energy_ip_supported(const qmc_handle* h);
 cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, const float* cache, float2* partial,
                              int nchunks, cudaStream_t st);

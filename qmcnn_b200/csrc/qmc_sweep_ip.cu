@@ -410,26 +410,40 @@ IpLaunch ip_launch_plan(const qmc_handle* h, int S) {
     return L;
 }
 
+// Time slicing of a sweep of n_steps for S chains on L's warp slots (host only): chunks of >= 64 steps, at most
+// ip_chunks (64) chunks per chain; one chunk when S fits the slots.  Returns the slice (task0 = 0) and the launch count.
+IpSlice ip_slice_plan(const qmc_handle* h, const IpLaunch& L, int S, long long n_steps, long long* launches) {
+    const long long slots = (long long)L.grid * L.warps;
+    long long chunks = 1;
+    if ((long long)S > slots) {
+        const long long cmax = h->ip_chunks > 0 ? h->ip_chunks : 64;     // at most this many chunks per chain
+        chunks = n_steps / 64;
+        if (chunks > cmax) chunks = cmax;
+        if (chunks < 1) chunks = 1;
+    }
+    IpSlice sl;
+    sl.group_warps = h->ip_group > 0 ? h->ip_group : 4;
+    sl.chunk_len = (n_steps + chunks - 1) / chunks;
+    sl.stagger = sl.chunk_len >= 64 ? h->ip_stagger * 1024 : 0;     // not worth ~40 us on a launch of a few steps
+    chunks = (n_steps + sl.chunk_len - 1) / sl.chunk_len;
+    sl.n_tasks = chunks * S;
+    sl.task0 = 0;
+    if (launches) *launches = (sl.n_tasks + slots - 1) / slots;
+    return sl;
+}
+
+void ip_slice_counts(const qmc_handle* h, const IpLaunch& L, int S, long long n_steps, long long* launches, long long* chunk_len) {
+    const IpSlice sl = ip_slice_plan(h, L, S, n_steps, launches);
+    if (chunk_len) *chunk_len = sl.chunk_len;
+}
+
 cudaError_t launch_sweep_ip(const qmc_handle* h, const SweepArgs& a, const IpLaunch& L, cudaStream_t st) {
     const int sy = h->ip_sync;
     // two instances are built: free-running (QMC_IP_SYNC=0, diagnosis) and phase groups (default).  Per-proposal
     // group barriers (1) and CTA-wide per-layer barriers (2) were measured (profiles/r01_summary.md) and dropped.
     cudaError_t e = cudaSuccess;
     const long long slots = (long long)L.grid * L.warps;
-    // time slicing: chunks of >= 64 steps, at most 64 chunks per chain; one chunk when S fits the slots
-    long long chunks = 1;
-    if ((long long)a.S > slots) {
-        const long long cmax = h->ip_chunks > 0 ? h->ip_chunks : 64;     // at most this many chunks per chain
-        chunks = a.n_steps / 64;
-        if (chunks > cmax) chunks = cmax;
-        if (chunks < 1) chunks = 1;
-    }
-    IpSlice sl;
-    sl.group_warps = h->ip_group > 0 ? h->ip_group : 4;
-    sl.chunk_len = (a.n_steps + chunks - 1) / chunks;
-    sl.stagger = sl.chunk_len >= 64 ? h->ip_stagger * 1024 : 0;     // not worth ~40 us on a launch of a few steps
-    chunks = (a.n_steps + sl.chunk_len - 1) / sl.chunk_len;
-    sl.n_tasks = chunks * a.S;
+    IpSlice sl = ip_slice_plan(h, L, a.S, a.n_steps, nullptr);
     for (sl.task0 = 0; sl.task0 < sl.n_tasks; sl.task0 += slots) {
         const long long left = sl.n_tasks - sl.task0;
         const long long ctas = ((left < slots ? left : slots) + L.warps - 1) / L.warps;
