@@ -235,6 +235,37 @@ def workload_name(name, cfg):
 
 
 # ------------------------------------------------------------------------------ CUDA arm
+ISSUE_PROFILES = {   # config: (ncu summary under profiles/, proposals of the captured launch = 200 sweep its x chains)
+    "C2": ("r02_k_sweep_w28_C2_metrics.txt", 200 * 4096),
+    "C4": ("r02_k_sweep_sym_C4_metrics.txt", 200 * 8192),
+}
+
+
+def issue_bound(name, proposals_per_s_per_gpu, num_sms, clk, root=None):
+    """Instruction-issue roofline of the sweep kernels whose captures are listed in ISSUE_PROFILES, or None.  Never raises:
+    the bench line must not depend on a profile file."""
+    try:
+        if name not in ISSUE_PROFILES:
+            return None
+        fn, nprop = ISSUE_PROFILES[name]
+        inst = None
+        for ln in open(os.path.join(root or ROOT, "profiles", fn)):
+            f = ln.split()
+            if len(f) >= 2 and f[0] == "smsp__inst_executed.sum":
+                inst = float(f[1])
+                break
+        mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz")
+        if not inst or not mhz:
+            return None
+        per_prop = inst / nprop
+        peak = num_sms * 4 * mhz * 1e6                    # one warp instruction per scheduler and cycle
+        return {"warp_instructions_per_proposal_from_profile": per_prop, "profile": "profiles/" + fn,
+                "peak_warp_instructions_per_s": peak, "achieved_warp_instructions_per_s": proposals_per_s_per_gpu * per_prop,
+                "frac": proposals_per_s_per_gpu * per_prop / peak}
+    except Exception:
+        return None
+
+
 def algorithmic_work_total(cfg):
     """Per proposal, incl. the symmetry images and the number of flipped sites (SURVEY 8d closed forms are per
     single-site window of one network)."""
@@ -440,6 +471,11 @@ def run_cuda(args, cfg, name):
                 except Exception:
                     pass
                 break
+        # C2 (small model, classic kernel) and C4 (symmetry sweep) are bound by instruction issue, not by FP32 / MUFU / HBM
+        # (profiles/r02_summary.md, "Classic kernels"): warp instructions per proposal of the committed ncu capture (NOT
+        # re-measured here) against what the SMs' four schedulers can issue at the clock this run saw
+        roofline["issue"] = issue_bound(name, proposals / (sw_ms * 1e-3) / world,
+                                        torch.cuda.get_device_properties(dev).multi_processor_count, clk)
         line = {
             "metric": "metropolis_proposals_per_s", "value": value, "unit": "proposals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
