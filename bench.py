@@ -474,8 +474,11 @@ def run_cuda(args, cfg, name):
         # C2 (small model, classic kernel) and C4 (symmetry sweep) are bound by instruction issue, not by FP32 / MUFU / HBM
         # (profiles/r02_summary.md, "Classic kernels"): warp instructions per proposal of the committed ncu capture (NOT
         # re-measured here) against what the SMs' four schedulers can issue at the clock this run saw
-        roofline["issue"] = issue_bound(name, proposals / (sw_ms * 1e-3) / world,
-                                        torch.cuda.get_device_properties(dev).multi_processor_count, clk)
+        try:
+            roofline["issue"] = issue_bound(name, proposals / (sw_ms * 1e-3) / world,
+                                            torch.cuda.get_device_properties(dev).multi_processor_count, clk)
+        except Exception:
+            roofline["issue"] = None
         line = {
             "metric": "metropolis_proposals_per_s", "value": value, "unit": "proposals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
