@@ -562,6 +562,7 @@ cudaError_t launch_energy_ip(const qmc_handle* h, const int8_t* spins, int N, co
 // phase cycles of k_sweep_ip since the last call (QMC_IP_PROFILE builds; zeros otherwise): out[0..7] cycles summed
 // over warps, out[8] proposals, out[9 + w] task duration of warp w of a CTA summed over CTAs and launches
 extern "C" int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/) {
+    if (!out) return QMC_ERR_BAD_ARGUMENT;
     for (int i = 0; i < qmc::kIpProfPhases + 13; ++i) out[i] = 0;
 #if QMC_IP_PROFILE
     cudaDeviceSynchronize();

@@ -62,3 +62,30 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_every_export_survives_null_arguments():
+    """The C ABI never throws, aborts or dereferences a null pointer: every entry point called with NULL pointers and zero
+    sizes returns (an error code, or 0 for the size queries).  In a subprocess: a crash must fail this test, not pytest."""
+    import subprocess
+    import sys
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from qmcnn_b200 import _lib
+lib = _lib.load()
+ints = (C.c_int, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t, C.c_longlong, C.c_ulonglong)
+for n in sorted(_lib.SIGNATURES):
+    res, args = _lib.SIGNATURES[n]
+    vals = [a(0) if a in ints else a(0.0) if a in (C.c_float, C.c_double) else None for a in args]
+    print("call", n, flush=True)
+    r = getattr(lib, n)(*vals)
+    if res is C.c_int and n not in ("qmc_destroy", "qmc_receptive_field"):      # (destroy(NULL) is a no-op; r is a query)
+        assert r < 0, (n, r)          # a null handle / descriptor / output is an error, never success
+    elif res in (C.c_size_t, C.c_int):
+        assert r == 0, (n, r)         # size / shape queries answer 0 without a handle
+print("survived", len(_lib.SIGNATURES))
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    last = [l for l in r.stdout.splitlines() if l.startswith("call")][-1:]
+    assert r.returncode == 0 and "survived" in r.stdout, "crashed or failed at %s: %s" % (last, r.stderr[-1500:])
