@@ -249,6 +249,11 @@ int qmc_diag_ip_profile(unsigned long long* out /*host, 21 entries*/);
  * bit-level mismatches (must be 0). */
 int qmc_diag_tanh_check(int device, unsigned long long* mismatches /*host*/);
 
+/* Host-only: the magic-number division every kernel's index arithmetic uses (FastDiv: x / d as one multiply-high for
+ * x < 65536, d < 65536; magics of d < 512 from a constant-memory table) against integer division - every x for the
+ * table's divisors, x around every multiple of d for the rest.  Number of mismatches (must be 0). */
+int qmc_diag_fastdiv_check(unsigned long long* mismatches /*host*/);
+
 /* Host-only (no CUDA call, works without a GPU): the launch qmc_metropolis_sweep would make for this model / lattice /
  * S chains / n_steps on a device with num_sms SMs and max_smem bytes of opt-in shared memory per CTA - the planner
  * behind Sampler.mcmc_op (sampler.py:158-177) as a testable function.  out[0] = kernel (QMC_PLAN_*), out[1] = CTAs,

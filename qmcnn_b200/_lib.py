@@ -96,6 +96,7 @@ SIGNATURES = {
     "qmc_diag_ip_profile": (_i, [C.POINTER(C.c_ulonglong)]),
     "qmc_diag_tanh_check": (_i, [_i, C.POINTER(C.c_ulonglong)]),
     "qmc_diag_sweep_plan": (_i, [C.POINTER(ModelDesc), _i, _i, C.c_int64, _i, C.c_size_t, C.POINTER(C.c_int64)]),
+    "qmc_diag_fastdiv_check": (_i, [C.POINTER(C.c_ulonglong)]),
     "qmc_launch_count": (C.c_ulonglong, []),
     "qmc_version": (C.c_char_p, []),
 }

@@ -145,6 +145,31 @@ int qmc_diag_sweep_plan(const qmc_model_desc* desc, int S, int num_flips, int64_
     return QMC_OK;
 }
 
+int qmc_diag_fastdiv_check(unsigned long long* mismatches) {
+    if (!mismatches) return fail(nullptr, QMC_ERR_BAD_ARGUMENT, "fastdiv_check: null output");
+    // host image of the constant-memory table (the same constexpr object the device copy is initialised from)
+    constexpr qmc::FastDivTable table = qmc::FastDivTable();
+    unsigned long long bad = 0;
+    auto mulhi = [](unsigned x, unsigned m) { return (unsigned)(((unsigned long long)x * m) >> 32); };
+    for (int d = 1; d < 65536; ++d) {
+        const unsigned M = qmc::fastdiv_magic(d);
+        if (d < qmc::kFastDivTable && table.v[d] != M) ++bad;
+        // FastDiv::div(x) = d > 1 ? umulhi(x, M) : x, for every x < 65536 at and around the multiples of d
+        for (int q = 0; q * d < 65536 + d; ++q)
+            for (int x = q * d - 1; x <= q * d + 1; ++x) {
+                if (x < 0 || x > 65535) continue;
+                const int got = d > 1 ? (int)mulhi((unsigned)x, M) : x;
+                if (got != x / d) ++bad;
+            }
+    }
+    // ... and exhaustively for the divisors the table serves
+    for (int d = 1; d < qmc::kFastDivTable; ++d)
+        for (int x = 0; x < 65536; ++x)
+            if ((d > 1 ? (int)mulhi((unsigned)x, table.v[d]) : x) != x / d) ++bad;
+    *mismatches = bad;
+    return QMC_OK;
+}
+
 const char* qmc_version(void) {
 #if QMC_DEBUG
     return "qmcnn_b200 0.2 (sm_100a, DEBUG build: device-side bounds checks)";

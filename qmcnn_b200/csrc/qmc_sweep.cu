@@ -16,7 +16,7 @@
 // tiles - the large-model variant), QMC_MAXW=16 (128 registers, small models) and QMC_MAXW=28
 // (72 registers, 7 warps per scheduler: models with <= 8 channels per layer, whose proposals
 // are a few thousand instructions of mostly latency - C2: 4096 chains are ONE wave of 148 x 28
-// warps, 135 -> 168 M proposals/s, profiles/r02_small_configs.md).
+// warps, 135 -> 168 M proposals/s, profiles/r02_summary.md, "Classic kernels").
 #ifndef QMC_MAXW
 #define QMC_MAXW 8
 #endif

@@ -89,3 +89,12 @@ print("survived", len(_lib.SIGNATURES))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     last = [l for l in r.stdout.splitlines() if l.startswith("call")][-1:]
     assert r.returncode == 0 and "survived" in r.stdout, "crashed or failed at %s: %s" % (last, r.stderr[-1500:])
+
+
+def test_fastdiv_magics_divide_exactly():
+    """Index arithmetic of every kernel: x / d as one multiply-high (FastDiv), magics of d < 512 from the constant-memory
+    table.  qmc_diag_fastdiv_check compares it with integer division on the host (same constexpr table)."""
+    from qmcnn_b200 import _lib
+    bad = ctypes.c_ulonglong(1)
+    assert _lib.load().qmc_diag_fastdiv_check(ctypes.byref(bad)) == 0
+    assert bad.value == 0
